@@ -1,0 +1,199 @@
+/*
+ * lgcu.h — C ABI of the B200-native (sm_100a) replacement for LegitEngine's per-pixel lighting and
+ * screen-space GI passes (the SSVGIRenderer hot path).
+ *
+ * Every entry point below replaces one SPIR-V full-screen pass (or a fused group of them) that the
+ * reference dispatches through legit::RenderGraph::AddPass. Citations are reference paths relative to
+ * the LegitEngine repository root (LV/ = dependencies/LegitVulkan/LegitVulkan/, SH/ = bin/data/Shaders/glsl/).
+ *
+ * Conventions
+ *  - Plain C, plain pointers and sizes. No torch / C++ types cross this boundary.
+ *  - All image pointers are DEVICE pointers. Parameter blocks (the reference's UBO structs) are HOST
+ *    pointers and are consumed (copied into kernel arguments) before the call returns.
+ *  - Every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *    stream). No host synchronisation, no allocation, no global state; safe to capture in a CUDA graph.
+ *  - Return value: LGCU_OK (0) or a negative lgcu_status. Nothing throws across the boundary.
+ *  - There is no CPU fallback: if no CUDA device / kernel image is usable the call returns
+ *    LGCU_ERR_CUDA and lgcu_last_error() describes why.
+ */
+#ifndef LGCU_H
+#define LGCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCU_ABI_VERSION 1
+#define LGCU_MAX_MIPS 16
+
+typedef enum lgcu_status {
+  LGCU_OK = 0,
+  LGCU_ERR_INVALID_ARGUMENT = -1, /* null pointer, size mismatch between bound images, bad radius ... */
+  LGCU_ERR_UNSUPPORTED_FORMAT = -2,
+  LGCU_ERR_CUDA = -3,             /* launch / runtime failure; see lgcu_last_error()                  */
+  LGCU_ERR_UNSUPPORTED = -4       /* a mode of the reference shader that has no live caller            */
+} lgcu_status;
+
+/* Formats: numeric values are the VkFormat enumerants the reference allocates its images with
+ * (src/Render/Renderers/SSVGIRenderer.h:393-404, LV/Swapchain.h:108). */
+typedef enum lgcu_format {
+  LGCU_FORMAT_UNDEFINED = 0,
+  LGCU_FORMAT_B8G8R8A8_SRGB = 50,
+  LGCU_FORMAT_R16G16B16A16_SFLOAT = 97,
+  LGCU_FORMAT_R32G32_SFLOAT = 103,
+  LGCU_FORMAT_R32G32B32A32_SFLOAT = 109, /* extension: fp32 render target for un-quantised parity checks */
+  LGCU_FORMAT_D32_SFLOAT = 126
+} lgcu_format;
+
+/* A resolved image view: what legit::RenderGraph::PassContext::GetImageView(id) hands to a pass
+ * (LV/RenderGraph.h:421-451, LV/ImageView.h:21-31, LV/Image.h:90-108), flattened to a POD.
+ * Memory layout: linear row-major texels, one contiguous block per mip level.
+ *   texel (x, y) of IMAGE level l lives at  base + levelOffset[l] + y * levelPitch[l] + x * texelSize.
+ * Level l has size (width >> l, height >> l) (integer floor; LV/RenderGraph.h:373-374).
+ * The view covers image levels [baseMip, baseMip + mipCount); shader "lod 0" == image level baseMip. */
+typedef struct lgcu_image {
+  void *base;
+  uint32_t format;        /* lgcu_format */
+  uint32_t width, height; /* size of IMAGE level 0 */
+  uint32_t imageMipCount; /* levels allocated in the image */
+  uint32_t baseMip;       /* view sub-range */
+  uint32_t mipCount;
+  uint32_t reserved0;
+  uint32_t reserved1;
+  uint64_t levelOffset[LGCU_MAX_MIPS]; /* bytes from base */
+  uint32_t levelPitch[LGCU_MAX_MIPS];  /* bytes per row   */
+} lgcu_image;
+
+/* Row range of the frame that this call computes: rows [y0, y1) of the BASE resolution (full-frame
+ * coordinates are kept everywhere: pattern index, uv, clamp-to-edge all use the full image size).
+ * NULL means the whole image. For passes that run on mip level l the range is scaled to
+ * [y0 >> l, ceil(y1 / 2^l)) clipped to the level. Used by the multi-GPU strip sharding. */
+typedef struct lgcu_rows {
+  uint32_t y0, y1;
+} lgcu_rows;
+
+/* ---- parameter blocks: byte-identical to the reference's tightly packed UBO structs ------------------ */
+#pragma pack(push, 1)
+/* column-major 4x4, like glm::mat4: m[c*4 + r] */
+typedef struct lgcu_mat4 { float m[16]; } lgcu_mat4;
+
+/* SSVGIRenderer.h:425-431 (GBufferBuilderShader::DataBuffer), SH/Common/gBufferBuilder.frag:4-10 */
+typedef struct lgcu_gbuffer_builder_data { lgcu_mat4 viewMatrix, projMatrix; float time, bla; } lgcu_gbuffer_builder_data;
+/* SSVGIRenderer.h:33-38 (DrawCallDataBuffer), SH/Common/gBufferBuilder.frag:12-17 */
+typedef struct lgcu_draw_call_data { lgcu_mat4 modelMatrix; float albedoColor[4]; float emissiveColor[4]; } lgcu_draw_call_data;
+/* SSVGIRenderer.h:457-464, SH/Common/directLighting.frag:4-11 */
+typedef struct lgcu_direct_lighting_data { lgcu_mat4 viewMatrix, projMatrix, lightViewMatrix, lightProjMatrix; float time; } lgcu_direct_lighting_data;
+/* MipBuilder.h:250-253, SH/Common/mipLevelBuilder.frag:4-7 */
+typedef struct lgcu_mip_level_builder_data { float filterType; } lgcu_mip_level_builder_data;
+/* BlurBuilder.h:63-67, SH/Common/blurLayerBuilder.frag:4-8 */
+typedef struct lgcu_blur_layer_builder_data { int32_t size[4]; int32_t radius; } lgcu_blur_layer_builder_data;
+/* SSVGIRenderer.h:476-481, SH/SSVGI/indirectLighting.frag:4-9 */
+typedef struct lgcu_indirect_lighting_data { lgcu_mat4 viewMatrix, projMatrix; float viewportExtent[4]; } lgcu_indirect_lighting_data;
+/* SSVGIRenderer.h:492-498, SH/Common/denoiser.frag:4-10 */
+typedef struct lgcu_denoiser_data { lgcu_mat4 viewMatrix, projMatrix; float viewportExtent[4]; int32_t radius; } lgcu_denoiser_data;
+/* SSVGIRenderer.h:509-513, SH/Common/finalGatherer.frag:4-8 */
+typedef struct lgcu_final_gatherer_data { lgcu_mat4 viewMatrix, projMatrix; } lgcu_final_gatherer_data;
+#pragma pack(pop)
+
+/* Per-pixel fragment attributes: the CUDA-side form of what the rasteriser hands to
+ * SH/Common/gBufferBuilder.frag (interpolated vertWorldPos / vertWorldNormal from gBufferBuilder.vert:32-40,
+ * the draw call the surviving fragment belongs to, and the depth-tested NDC z). 32 bytes per pixel,
+ * row-major, `attribPitch` bytes per row. objectId == LGCU_NO_OBJECT marks an uncovered pixel, which keeps
+ * the attachment clear values (LV/RenderGraph.h:466-469, 484-487). */
+typedef struct lgcu_fragment {
+  float worldPos[3];
+  float worldNormal[3];
+  uint32_t objectId;
+  float ndcDepth;
+} lgcu_fragment;
+#define LGCU_NO_OBJECT 0xFFFFFFFFu
+
+/* Clear values of the G-buffer pass (default colour clear (1, .5, 0, 1), depth 1; LV/RenderGraph.h:469, 487) */
+typedef struct lgcu_clear_values { float color[4]; float depth; } lgcu_clear_values;
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+int lgcu_abi_version(void);
+/* Human-readable description of the last error raised on the calling thread ("" if none). */
+const char *lgcu_last_error(void);
+/* Bytes per texel of a format, 0 if unsupported. */
+uint32_t lgcu_format_texel_size(uint32_t format);
+/* Fills width/height/levelOffset/levelPitch for a `mips`-level image in the library's canonical layout
+ * (pitch rounded up to 128 B, level blocks to 256 B) and returns the allocation size in bytes. `base` and the
+ * view range are left for the caller. Host-only helper; does not touch the device. */
+uint64_t lgcu_image_layout(lgcu_image *img, uint32_t format, uint32_t width, uint32_t height, uint32_t mips);
+
+/* ---- one entry point per reference pass ------------------------------------------------------------- */
+
+/* K1 "GBufferPass" fragment stage: SH/Common/gBufferBuilder.frag:28-38, pass SSVGIRenderer.h:107-158.
+ * objects: DEVICE array of nObjects DrawCallData blocks (one per draw call, indexed by lgcu_fragment.objectId).
+ * Writes albedo, emissive, normal (RGBA16F), depthMoments level 0 (RG32F) and depthStencil (D32F). */
+int lgcu_gbuffer_resolve(const lgcu_gbuffer_builder_data *params, const lgcu_draw_call_data *objects, uint32_t nObjects,
+                         const lgcu_fragment *fragments, uint64_t fragmentPitchBytes, const lgcu_clear_values *clear,
+                         const lgcu_image *albedo, const lgcu_image *emissive, const lgcu_image *normal,
+                         const lgcu_image *depthMoments, const lgcu_image *depthStencil, const lgcu_rows *rows, void *stream);
+
+/* K2 "LightPass": SH/Common/directLighting.frag:45-83, pass SSVGIRenderer.h:161-205. */
+int lgcu_direct_light(const lgcu_direct_lighting_data *params, const lgcu_image *albedo, const lgcu_image *emissive,
+                      const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *shadowMap,
+                      const lgcu_image *directLight, const lgcu_rows *rows, void *stream);
+
+/* K3 "MipBuilderPass" (one level): SH/Common/mipLevelBuilder.frag:17-43, driver MipBuilder.h:142-181.
+ * src and dst are single-level views (level l-1 and l). filterType >= 0.5 (Depth) has no live caller and
+ * returns LGCU_ERR_UNSUPPORTED. */
+int lgcu_mip_level(const lgcu_mip_level_builder_data *params, const lgcu_image *srcLevel, const lgcu_image *dstLevel,
+                   const lgcu_rows *rows, void *stream);
+
+/* K4 "BlurPass" (one level): SH/Common/blurLayerBuilder.frag:17-35, driver BlurBuilder.h:14-46.
+ * radius 0 = copy, radius 2 = asymmetric 4x4 box (-2..+1) with clamp-to-edge. Other radii: generic loop. */
+int lgcu_blur_level(const lgcu_blur_layer_builder_data *params, const lgcu_image *srcLevel, const lgcu_image *dstLevel,
+                    const lgcu_rows *rows, void *stream);
+
+/* K5 "IndirectLightPass": SH/SSVGI/indirectLighting.frag:114-272, pass SSVGIRenderer.h:224-263.
+ * flags: LGCU_GI_* below. */
+int lgcu_gi_gather(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight,
+                   const lgcu_image *blurredDepthMoments, const lgcu_image *normal, const lgcu_image *depthStencil,
+                   const lgcu_image *indirectLight, uint32_t flags, const lgcu_rows *rows, void *stream);
+#define LGCU_GI_DEFAULT 0u
+#define LGCU_GI_STRICT 1u /* shader-order arithmetic with libm-grade sin/cos/atan/pow/log (parity variant) */
+
+/* K6 "DenoiserPass": SH/Common/denoiser.frag:72-185, pass SSVGIRenderer.h:266-302.
+ * `depthMoments` is what the reference binds to the shader's depthStencilSampler (SSVGIRenderer.h:293). */
+int lgcu_denoise(const lgcu_denoiser_data *params, const lgcu_image *noisy, const lgcu_image *normal,
+                 const lgcu_image *depthMoments, const lgcu_image *denoised, const lgcu_rows *rows, void *stream);
+
+/* K7 "GatheringPass": SH/Common/finalGatherer.frag:42-60, pass SSVGIRenderer.h:305-342. */
+int lgcu_final_gather(const lgcu_final_gatherer_data *params, const lgcu_image *directLight,
+                      const lgcu_image *blurredDirectLight, const lgcu_image *albedo, const lgcu_image *indirectLight,
+                      const lgcu_image *swapchain, const lgcu_rows *rows, void *stream);
+
+/* ---- fused groups (same outputs as the passes they replace, fewer trips through HBM) ------------------ */
+
+/* K1+K2: G-buffer resolve and direct lighting in one pass over the fragments. Writes everything K1 writes
+ * plus directLight level 0. */
+int lgcu_gbuffer_direct_light(const lgcu_gbuffer_builder_data *gparams, const lgcu_direct_lighting_data *lparams,
+                              const lgcu_draw_call_data *objects, uint32_t nObjects, const lgcu_fragment *fragments,
+                              uint64_t fragmentPitchBytes, const lgcu_clear_values *clear, const lgcu_image *albedo,
+                              const lgcu_image *emissive, const lgcu_image *normal, const lgcu_image *depthMoments,
+                              const lgcu_image *depthStencil, const lgcu_image *shadowMap, const lgcu_image *directLight,
+                              const lgcu_rows *rows, void *stream);
+
+/* K3+K4 for one chain: builds levels 1..mips-1 of `chain` from its level 0 (MipBuilder::BuildMips, Avg filter)
+ * and writes blurred[l] = blur(chain[l]) with radius 0 at level 0 and `radius` at levels >= 1
+ * (SSVGIRenderer.h:207-221). `chain` and `blurred` are whole-image views with identical format and size. */
+int lgcu_mip_blur_chain(const lgcu_image *chain, const lgcu_image *blurred, int32_t radius, const lgcu_rows *rows,
+                        void *stream);
+
+/* K6(radius 0)+K7: denoised = noisy; swapchain = directLight + denoised * albedo. */
+int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_final_gatherer_data *fparams,
+                              const lgcu_image *noisy, const lgcu_image *normal, const lgcu_image *depthMoments,
+                              const lgcu_image *denoised, const lgcu_image *directLight,
+                              const lgcu_image *blurredDirectLight, const lgcu_image *albedo,
+                              const lgcu_image *swapchain, const lgcu_rows *rows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCU_H */
