@@ -1,0 +1,118 @@
+// lgcu_kernels.h — host-callable launchers of the SSVGI CUDA kernels (internal to liblgcu.so).
+// Argument blocks carry already-validated device views and the per-frame constants that the C ABI layer
+// (lgcu_api.cu) hoists out of the reference's per-fragment code.
+#pragma once
+
+#include "lgcu_device.cuh"
+
+namespace lgcu {
+
+struct ClearValues {
+  float color[4];
+  float depth;
+};
+
+struct GBufferArgs {
+  const lgcu_fragment *fragments;
+  uint64_t fragmentPitch;
+  const lgcu_draw_call_data *objects;
+  uint32_t nObjects;
+  float cam[3]; // (inverse(viewMatrix) * (0,0,0,1)).xyz  — gBufferBuilder.frag:30
+  ClearValues clear;
+  LevelView albedo, emissive, normal, depthMoments, depthStencil;
+  RowRange rows;
+};
+
+struct DirectLightArgs {
+  Mat4 invViewProj;   // inverse(projMatrix * viewMatrix)          directLighting.frag:50-52
+  Mat4 lightViewProj; // lightProjMatrix * lightViewMatrix         directLighting.frag:60
+  Mat4 lightView;     //                                            directLighting.frag:62
+  float lightPos[3];  // (inverse(lightViewMatrix) * (0,0,0,1)).xyz directLighting.frag:54
+  LevelView albedo, emissive, normal, depthStencil, shadowMap, directLight;
+  RowRange rows;
+};
+
+struct MipLevelArgs {
+  uint32_t format;
+  LevelView src, dst;
+  RowRange rows; // in dst rows
+};
+
+struct BlurLevelArgs {
+  uint32_t format;
+  int sizeX, sizeY, radius; // BlurLayerBuilderData
+  LevelView src, dst;
+  RowRange rows; // in dst rows
+};
+
+struct ChainArgs { // fused K3+K4 over one chain
+  uint32_t format;
+  int levels; // levels present (<= kMaxGatherLevels)
+  int radius;
+  PyramidView chain, blurred;
+  RowRange rows; // base rows
+};
+
+constexpr int kGatherDirs = 4;     // indirectLighting.frag:166
+constexpr int kGatherMaxSteps = 16; // table capacity for the march (8 steps are reached at 8K)
+
+// Per-frame tables of the GI gather. Everything in here is a pure function of viewportSize.x and is evaluated on
+// the host with the same libm calls the reference arithmetic makes, so pattern / step / LOD selection is
+// bit-identical to the oracle ("int pattern index, iters, mip level select bit-exact").
+struct GatherTables {
+  float dirX[16][kGatherDirs], dirY[16][kGatherDirs]; // cos/sin(1.57075*ang + 1.57075*d)   :177-178
+  float pixelOffset[16][kGatherMaxSteps];             // near*pow(2.57075, k+lin)+1-near      :217
+  float lod[16][kGatherMaxSteps];                     // log(max(0,...))/ln2 - 2, clamped to [0, levels-1]  :234-235
+  float iterThreshold[kGatherMaxSteps];               // smallest |tmax| for which iterationsCount > n  :212
+  int maxSteps;
+};
+
+struct GatherArgs {
+  Mat4 invViewProj; // :123
+  float cam[3];     // :127
+  float viewport[2];
+  uint32_t outFormat; // RGBA16F or RGBA32F
+  PyramidView light;   // blurredDirectLight  (RGBA16F)
+  PyramidView moments; // blurredDepthMoments (RG32F)
+  LevelView normal, depthStencil, indirect;
+  RowRange rows;
+};
+
+struct DenoiseArgs {
+  uint32_t format; // noisy/denoised format
+  int radius;
+  float viewport[2];
+  LevelView noisy, depthMoments, denoised;
+  RowRange rows;
+};
+
+struct FinalGatherArgs {
+  uint32_t indirectFormat;
+  LevelView directLight, albedo, indirect, swapchain;
+  RowRange rows;
+};
+
+struct DenoiseFinalArgs { // fused K6 (radius 0) + K7
+  uint32_t indirectFormat;
+  LevelView noisy, denoised, directLight, albedo, swapchain;
+  RowRange rows;
+};
+
+struct GBufferLightArgs { // fused K1 + K2
+  GBufferArgs g;
+  DirectLightArgs l;
+};
+
+cudaError_t launchGBufferResolve(const GBufferArgs &a, cudaStream_t s);
+cudaError_t launchDirectLight(const DirectLightArgs &a, cudaStream_t s);
+cudaError_t launchGBufferDirectLight(const GBufferLightArgs &a, cudaStream_t s);
+cudaError_t launchMipLevel(const MipLevelArgs &a, cudaStream_t s);
+cudaError_t launchBlurLevel(const BlurLevelArgs &a, cudaStream_t s);
+cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s);
+cudaError_t launchGatherStrict(const GatherArgs &a, const GatherTables &t, cudaStream_t s);
+cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, cudaStream_t s);
+cudaError_t launchDenoise(const DenoiseArgs &a, cudaStream_t s);
+cudaError_t launchFinalGather(const FinalGatherArgs &a, cudaStream_t s);
+cudaError_t launchDenoiseFinalGather(const DenoiseFinalArgs &a, cudaStream_t s);
+
+} // namespace lgcu

@@ -1,0 +1,77 @@
+"""Shared helpers for the parity tests: oracle frames, device upload/download, comparison metrics."""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+from typing import Dict, Tuple
+
+import numpy as np
+
+from legitengine_b200 import abi, images, passes, scene
+from oracle import loader
+
+F16_EPS = 2.0 ** -10  # one fp16 ulp, relative (upper bound)
+
+
+@functools.lru_cache(maxsize=8)
+def oracle_frame(seed: int, width: int, height: int, denoise_radius: int = 0, n_boxes: int = 64, indirect_format: int = abi.FORMAT_R16G16B16A16_SFLOAT,
+                 shadow_size: int = 1024):
+    """Scene + the port oracle's images for the whole frame (cached: several tests share one frame)."""
+    sc = scene.make_scene(seed, width, height, n_boxes=n_boxes, shadow_size=shadow_size)
+    p = passes.make_params(width, height, sc.matrices, denoise_radius)
+    fi = passes.FrameImages(width, height, images.HostImage, indirect_format=indirect_format, shadow_size=shadow_size)
+    inp = passes.upload_inputs(fi, sc)
+    passes.run_pass_list(loader.port(), fi, p, inp)
+    return sc, p, fi
+
+
+def device_frame_like(host: passes.FrameImages, copy=()) -> passes.FrameImages:
+    """Device images with the same declaration as `host`; images named in `copy` are uploaded, the rest poisoned."""
+    import torch
+
+    dev = passes.FrameImages(host.width, host.height, images.DeviceImage, kwargs={"device": "cuda:0"}, indirect_format=host.indirect_format,
+                             shadow_size=host.shadow_size)
+    for name in copy:
+        getattr(dev, name).tensor.copy_(torch.from_numpy(getattr(host, name).buf))
+    return dev
+
+
+def psnr(a: np.ndarray, b: np.ndarray, peak: float | None = None) -> float:
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    mse = float(np.mean((a - b) ** 2))
+    if mse == 0.0:
+        return float("inf")
+    if peak is None:
+        peak = max(float(np.max(np.abs(b))), 1e-12)
+    return 10.0 * np.log10(peak * peak / mse)
+
+
+def compare_level(cuda_img: images.HostImage, ref_img: images.HostImage, level: int = 0) -> Dict[str, float]:
+    a, b = cuda_img.level_f32(level), ref_img.level_f32(level)
+    raw_equal = np.all(cuda_img.level_bytes(level) == ref_img.level_bytes(level), axis=2)
+    diff = np.abs(a - b)
+    finite = np.isfinite(a) & np.isfinite(b)
+    diff = np.where(finite, diff, np.where(np.isnan(a) == np.isnan(b), 0.0, np.inf))
+    tol = np.maximum(1e-3, F16_EPS * np.abs(b))
+    return {
+        "texels": raw_equal.size,
+        "mismatched_texels": int((~raw_equal).sum()),
+        "max_abs": float(diff.max()) if diff.size else 0.0,
+        "outside_tol": int((diff > tol).any(axis=2).sum()),
+        "psnr": psnr(a, b),
+    }
+
+
+def assert_bit_exact(cuda_img, ref_img, level=0, what=""):
+    r = compare_level(cuda_img, ref_img, level)
+    assert r["mismatched_texels"] == 0, f"{what} level {level}: {r}"
+
+
+def assert_close(cuda_img, ref_img, level=0, what="", max_outside_frac=1e-4, min_psnr=60.0):
+    """North-star tolerance: max-abs 1e-3 (or one fp16 ulp of the value where that is larger, for fp16-stored HDR radiance)
+    on all but `max_outside_frac` of the texels, and PSNR >= 60 dB."""
+    r = compare_level(cuda_img, ref_img, level)
+    assert r["outside_tol"] <= max_outside_frac * r["texels"], f"{what} level {level}: {r}"
+    assert r["psnr"] >= min_psnr, f"{what} level {level}: {r}"
+    return r
