@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — full SSVGI GI frame (G-buffer resolve -> direct light -> mip build -> blur -> GI gather -> denoise -> final
+gather) on B200, measured as BASELINE.json's metric: frame ms and Mpix/s, with the HBM roofline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 4k|8k|1080p|WxH] [--impl ours|reference]
+
+One "step" = one frame of the workload through the C++ rendergraph harness (liblegit_cuda.so -> liblgcu.so kernels).
+  value : whole-job Mpix/s with the rasterised scene already resident in HBM (CUDA-graph replay of the fused frame)
+  e2e   : same frame driven from HOST buffers: every step copies the fragment buffer host->device from pinned memory,
+          renders, and copies the BGRA8 swapchain image device->host, all inside the timed region
+N > 1   : one process per GPU (torchrun); independent frames per GPU (BASELINE configs[4], "weak"), no data-path collective
+--impl reference : the reference's own SPIR-V passes on the host cores (oracle/_ref, else the C port), bounded sample.
+The CPU oracle is used here ONLY for the cpu_baseline / reference legs — never on the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {"4k": (3840, 2160), "8k": (7680, 4320), "1080p": (1920, 1080), "512": (512, 512)}
+# pass-granular algorithmic bytes per base pixel (SURVEY.md §8d / BASELINE.md §3)
+BYTES_PER_PX = {"resolve": 68.0, "light": 36.0, "mips": 26.67, "blur": 42.67, "gather": 41.33, "denoise": 16.0, "final": 28.0}
+FRAME_BYTES_PER_PX = 258.67
+SHADOW_MAP_BYTES = 4 * 1024 * 1024
+METRIC = "full_gi_frame_mpix_per_s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", default="4k")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "passes"])
+    ap.add_argument("--strict", action="store_true", help="use the shader-order parity gather kernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 30))")
+    return ap.parse_args()
+
+
+def workload_size(name: str):
+    if name in WORKLOADS:
+        return WORKLOADS[name]
+    w, h = name.lower().split("x")
+    return int(w), int(h)
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons during the timed region (NVML, ~20 ms period)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU legs
+def cpu_frame_seconds(width: int, height: int, frames: int, warmup: int = 1):
+    """Times the reference's SPIR-V passes (oracle/_ref; the C port if the reference arm is not built) on the host cores."""
+    from legitengine_b200 import images, passes, scene
+    from oracle import loader
+
+    be = loader.ref() if loader.have_ref() else loader.port()
+    sc = scene.make_scene(0xC0FFEE, width, height)
+    p = passes.make_params(width, height, sc.matrices, 0)
+    fi = passes.FrameImages(width, height, images.HostImage)
+    inp = passes.upload_inputs(fi, sc)
+    for _ in range(warmup):
+        passes.run_pass_list(be, fi, p, inp)
+    times = []
+    for _ in range(frames):
+        t0 = time.perf_counter()
+        passes.run_pass_list(be, fi, p, inp)
+        times.append(time.perf_counter() - t0)
+    return be.kind, int(be.num_threads()), times
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    W, H = workload_size(args.workload)
+    sw, sh = max(W // 4, 64), max(H // 4, 36)  # bounded sample: 1/16 of the pixels per step
+    kind, cores, times = cpu_frame_seconds(sw, sh, args.steps, min(args.warmup, 1))
+    sec = float(np.mean(times))
+    value = sw * sh / sec / 1e6
+    sample = f"{sw}x{sh} full frame (1/16 of the {W}x{H} pixels) per step, same synthetic scene generator, all passes K1..K7"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W}x{H} full GI frame (BASELINE configs[2] + G-buffer resolve), CPU sample: {sample}",
+                   "what": "reference SPIR-V passes (spirv-cross C++ backend + glm) on host cores" if kind == "reference" else "plain-C port of the reference shaders on host cores"},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    from legitengine_b200 import abi, harness, scene
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    W, H = workload_size(args.workload)
+    npx = W * H
+    mode = harness.MODE_FUSED if args.mode == "fused" else harness.MODE_PASS_GRANULAR
+    gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
+
+    # synthetic rasterised scene (seed differs per rank: independent frames), generated on the host into pinned memory
+    m = scene.frame_matrices(W, H)
+    seed = 0xC0FFEE + rank
+    frag_host = torch.empty((H, W * 32), dtype=torch.uint8).pin_memory()
+    frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(H, W)
+    scene.scene_fragments(seed, W, H, m, out=frags)
+    objects = scene.scene_objects(seed)
+    shadow = torch.from_numpy(scene.scene_shadow_map(seed, m)).pin_memory()
+    swap_host = torch.empty((H, W * 4), dtype=torch.uint8).pin_memory()
+
+    stream = torch.cuda.Stream()
+    r = harness.Renderer(W, H, stream=stream.cuda_stream)
+    r.upload_fragments(frag_host.data_ptr(), W * 32)
+    r.upload_objects(objects.ctypes.data, len(objects))
+    r.upload_light_depth(shadow.data_ptr(), 1024)
+    r.sync()
+
+    # first frame allocates the images; per-pass GPU profile of the un-captured frame (events between passes)
+    r.render_frame(mode, 0, gi_flags)
+    r.sync()
+    pass_ms = {}
+    prof_frames = 5
+    for _ in range(prof_frames):
+        r.render_frame(mode, 0, gi_flags, profile=True)
+        r.sync()
+        for name, ms in r.profile():
+            pass_ms[name] = pass_ms.get(name, 0.0) + ms / prof_frames
+    passes_per_frame = r.last_pass_count()
+
+    r.capture_frame(mode, 0, gi_flags)
+    kernels_per_frame = r.captured_kernel_count()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(steps):
+                fn()
+            ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    # --- value: device-resident inputs, CUDA-graph replay
+    ms_total, clocks = timed(r.replay_frame, args.steps, max(args.warmup, 3), sample_clocks=True)
+    ms_per_step = ms_total / args.steps
+    value = world * npx / (ms_per_step * 1e-3) / 1e6
+
+    # --- e2e: host fragments in, swapchain out, every step
+    def e2e_step():
+        r.upload_fragments(frag_host.data_ptr(), W * 32)
+        r.replay_frame()
+        r.download_swapchain(swap_host.data_ptr(), W * 4)
+
+    e2e_steps = args.e2e_steps or min(args.steps, 30)
+    e2e_ms, _ = timed(e2e_step, e2e_steps, 3)
+    e2e_value = world * npx / (e2e_ms / e2e_steps * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        gather_ms = pass_ms.get("IndirectLightPass", 0.0)
+        gather_bytes = BYTES_PER_PX["gather"] * npx
+        frame_bytes = FRAME_BYTES_PER_PX * npx + SHADOW_MAP_BYTES
+        roofline = {
+            "kernel": "gi_gather (IndirectLightPass)", "bound": "hbm", "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
+            "peak": peak, "unit": "GB/s", "frac": (gather_bytes / (gather_ms * 1e-3) / 1e9 / peak) if gather_ms else None, "traffic": None,
+            "peak_source": peak_src, "ms": gather_ms,
+            "note": "the gather is FP32-ALU/L1 bound, not HBM bound (SURVEY.md F7): achieved = 41.33 B/px compulsory bytes / its measured time",
+        }
+        roofline_frame = {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "algorithmic_bytes": frame_bytes,
+                          "note": "whole frame, pass-granular algorithmic bytes 258.67 B/px + 4 MiB shadow map"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{W}x{H} full GI frame: G-buffer resolve + shadow-mapped direct light + 2x9 mip levels + 2x10 blur levels + SSVGI gather + denoise(r=0) + final gather (BASELINE configs[2] incl. resolve)"
+                            + (f"; {world} GPUs render independent frames (configs[4] throughput mode)" if world > 1 else ""),
+                "pass_list": "fused (K1+K2, mip+blur chain x2, K5, K6+K7)" if mode == harness.MODE_FUSED else "pass-granular (reference's 46 passes)",
+                "gather_kernel": "strict" if args.strict else "fast", "cuda_graph": True, "passes_per_frame": passes_per_frame,
+                "l2": "inputs larger than L2 (frame working set %.0f MB vs 126 MB L2)" % (r.allocated_bytes() / 1e6),
+                "storage": "RGBA16F / RG32F / D32F / BGRA8 images exactly as the reference allocates them",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": kernels_per_frame * args.steps,
+            "kernels_per_frame": kernels_per_frame,
+            "roofline": roofline,
+            "roofline_frame": roofline_frame,
+            "pass_ms": {k: round(v, 4) for k, v in pass_ms.items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sw, sh = W // 2, H // 2
+            kind, cores, times = cpu_frame_seconds(sw, sh, 2, 1)
+            sec = float(np.mean(times))
+            line["cpu_baseline"] = {"value": sw * sh / sec / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                                    "sample": f"{sw}x{sh} full frame (1/4 of the pixels), mean of 2 frames after 1 warm-up, {sec:.2f} s/frame"}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

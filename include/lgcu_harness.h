@@ -1,0 +1,70 @@
+/*
+ * lgcu_harness.h — C ABI of the headless frame harness (liblegit_cuda.so).
+ *
+ * The harness stands where the reference's application shell stands (src/main.cpp:104-320: create the renderer, recreate
+ * the viewport resources, then per frame BeginFrame -> renderer->RenderFrame -> EndFrame -> RenderGraph::Execute): it owns
+ * a legit_cuda::Core + SSVGIRenderer (the C++ mirror of the reference's rendergraph / renderer, host/legit_cuda/), the
+ * rasterised scene buffers and a B8G8R8A8_SRGB "swapchain" image, and runs one frame per call on a CUDA stream.
+ * Python (tests, bench.py) drives it through ctypes; a C++ application would use the legit_cuda headers directly.
+ *
+ * All calls enqueue on the renderer's stream and return; lgh_sync() waits. Host pointers given to the upload/download
+ * calls should be page-locked for the copies to be asynchronous. Return value: 0 or a negative lgcu_status; the message
+ * is available from lgh_last_error().
+ */
+#ifndef LGCU_HARNESS_H
+#define LGCU_HARNESS_H
+
+#include "lgcu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lgh_renderer lgh_renderer;
+
+enum { LGH_MODE_PASS_GRANULAR = 0, LGH_MODE_FUSED = 1 };
+
+const char *lgh_last_error(void);
+
+/* stream: cudaStream_t to run on (NULL = a stream owned by the harness). The device is the calling thread's current one. */
+lgh_renderer *lgh_create(uint32_t width, uint32_t height, void *stream);
+void lgh_destroy(lgh_renderer *r);
+
+/* camera / light as (position, vertAngle, horAngle) — src/Scene/Scene.h:20-34; defaults are the reference's (main.cpp:166-172) */
+int lgh_set_camera(lgh_renderer *r, const float camPos[3], float camVertAngle, float camHorAngle, const float lightPos[3],
+                   float lightVertAngle, float lightHorAngle);
+
+/* scene upload (host -> device, async). rows [rowBegin,rowEnd) of the fragment buffer; hostFragments points at row 0. */
+int lgh_upload_fragments(lgh_renderer *r, const lgcu_fragment *hostFragments, uint64_t hostPitchBytes, uint32_t rowBegin, uint32_t rowEnd);
+int lgh_upload_objects(lgh_renderer *r, const lgcu_draw_call_data *hostObjects, uint32_t count);
+int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t size);
+
+/* One frame: SSVGIRenderer::RenderFrame + RenderGraph::Execute. rows may be NULL (whole frame; required for pass-granular).
+ * profile != 0 records per-pass GPU events (read them with lgh_get_profile after lgh_sync). */
+int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile);
+
+/* Capture the same frame into a CUDA graph once (after at least one lgh_render_frame with the same arguments has
+ * allocated the images), then replay it with a single launch per frame. */
+int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows);
+int lgh_replay_frame(lgh_renderer *r);
+/* kernel nodes in the captured graph / passes declared by the last lgh_render_frame */
+int lgh_captured_kernel_count(lgh_renderer *r);
+int lgh_last_pass_count(lgh_renderer *r);
+
+/* images by name: albedo emissive normal depthMoments blurredDepthMoments depthStencil directLight blurredDirectLight
+ * shadowMap indirectLight denoisedIndirectLight swapchain. Valid after the first frame. */
+int lgh_image_desc(lgh_renderer *r, const char *name, lgcu_image *out);
+int lgh_download_image(lgh_renderer *r, const char *name, uint32_t level, void *host, uint64_t hostPitchBytes, uint32_t rowBegin, uint32_t rowEnd);
+
+int lgh_sync(lgh_renderer *r);
+
+/* Per-pass GPU times of the last profiled frame: names are written '\n'-separated into nameBuf, durations (ms) into ms.
+ * Returns the number of passes (or a negative status). */
+int lgh_get_profile(lgh_renderer *r, char *nameBuf, uint64_t nameBufBytes, float *ms, uint32_t maxPasses);
+
+uint64_t lgh_allocated_bytes(lgh_renderer *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -78,6 +78,18 @@ def build_scene(force: bool = False) -> Path:
     return out
 
 
+def build_host(force: bool = False) -> Path:
+    """liblegit_cuda.so: the C++ rendergraph / renderer mirror + headless harness (host code; links liblgcu.so)."""
+    LIB.mkdir(exist_ok=True)
+    out = LIB / "liblegit_cuda.so"
+    src = HOST / "harness.cpp"
+    deps = [src, ROOT / "include" / "lgcu.h", ROOT / "include" / "lgcu_harness.h", LIB / "liblgcu.so"] + list((HOST / "legit_cuda").glob("*.h")) + [CSRC / "lgcu_mat4.h"]
+    if force or _stale(out, deps):
+        _run([NVCC, "-shared", "-O2", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", f"-I{HOST}", "-o", out, src,
+              f"-L{LIB}", "-llgcu", "-Xlinker", "-rpath=$ORIGIN"])
+    return out
+
+
 def build_oracle() -> None:
     env = dict(os.environ)
     _run(["make", "-C", ROOT / "oracle", "port"], env=env)
@@ -87,6 +99,7 @@ def build_oracle() -> None:
 
 def build_all(force: bool = False) -> None:
     build_cuda(force)
+    build_host(force)
     build_scene(force)
     build_oracle()
 

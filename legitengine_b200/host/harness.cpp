@@ -1,0 +1,312 @@
+// harness.cpp — headless frame harness over the legit_cuda renderer (C ABI in include/lgcu_harness.h).
+// Plays the role of the reference's frame loop (src/main.cpp:197-312 + LV/PresentQueue.h:85-166): per frame it maps the
+// shader memory pool, lets SSVGIRenderer::RenderFrame declare the passes and runs RenderGraph::Execute on the stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lgcu_harness.h"
+#include "legit_cuda/SSVGIRenderer.h"
+
+using namespace legit_cuda;
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int setError(int status, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+} // namespace
+
+struct lgh_renderer {
+  uint32_t width = 0, height = 0;
+  cudaStream_t stream = nullptr;
+  bool ownsStream = false;
+  std::unique_ptr<Core> core;
+  std::unique_ptr<SSVGIRenderer> renderer;
+  ShaderMemoryPool memoryPool;
+  CpuProfiler cpuProfiler;
+  GpuProfiler gpuProfiler;
+  bool profiled = false;
+  int lastPassCount = 0;
+
+  std::unique_ptr<Buffer> fragments, objects, lightDepth;
+  uint32_t objectCapacity = 0, objectCount = 0, lightDepthSize = 0;
+  std::unique_ptr<Scene> scene;
+
+  std::unique_ptr<ImageData> swapchainImage;
+  std::unique_ptr<ImageView> swapchainView;
+  RenderGraph::ImageViewProxyUnique swapchainProxy;
+
+  Camera camera = DefaultCamera(), light = DefaultLight();
+
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graphExec = nullptr;
+  int graphKernels = 0;
+
+  uint64_t fragmentPitch() const { return uint64_t(width) * sizeof(lgcu_fragment); }
+
+  void ensureScene() {
+    if (!lightDepth) {
+      lightDepthSize = 1024;
+      lightDepth.reset(new Buffer(size_t(lightDepthSize) * lightDepthSize * 4));
+    }
+    if (!objects) {
+      objectCapacity = 4096;
+      objects.reset(new Buffer(size_t(objectCapacity) * sizeof(lgcu_draw_call_data)));
+    }
+    if (!scene) scene.reset(new Scene(core->GetRenderGraph(), fragments.get(), fragmentPitch(), objects.get(), objectCount, lightDepth.get(), lightDepthSize));
+    scene->objectsCount = objectCount;
+    scene->lightDepthSize = lightDepthSize;
+  }
+
+  void declareAndExecute(uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, bool profile) {
+    ensureScene();
+    memoryPool.MapBuffer();
+    FrameInfo frameInfo;
+    frameInfo.memoryPool = &memoryPool;
+    frameInfo.swapchainImageViewProxyId = swapchainProxy->Id();
+    FrameOptions options;
+    options.mode = mode == LGH_MODE_PASS_GRANULAR ? FrameOptions::Mode::PassGranular : FrameOptions::Mode::Fused;
+    options.denoiserRadius = denoiserRadius;
+    options.giFlags = giFlags;
+    if (rows) {
+      options.useRows = true;
+      options.rows = *rows;
+    }
+    renderer->RenderFrame(frameInfo, camera, light, scene.get(), options);
+    lastPassCount = int(core->GetRenderGraph()->GetPendingPassCount());
+    core->GetRenderGraph()->Execute(stream, profile ? &cpuProfiler : nullptr, profile ? &gpuProfiler : nullptr);
+    profiled = profile;
+  }
+
+  ImageView *findImage(const std::string &name) {
+    auto *res = renderer->GetViewportResources();
+    RenderGraph *g = core->GetRenderGraph();
+    if (name == "swapchain") return swapchainView.get();
+    if (name == "albedo") return g->GetResolvedImageView(res->albedo.imageViewProxy->Id());
+    if (name == "emissive") return g->GetResolvedImageView(res->emissive.imageViewProxy->Id());
+    if (name == "normal") return g->GetResolvedImageView(res->normal.imageViewProxy->Id());
+    if (name == "depthMoments") return g->GetResolvedImageView(res->depthMoments.imageViewProxy->Id());
+    if (name == "blurredDepthMoments") return g->GetResolvedImageView(res->blurredDepthMoments.imageViewProxy->Id());
+    if (name == "depthStencil") return g->GetResolvedImageView(res->depthStencil.imageViewProxy->Id());
+    if (name == "directLight") return g->GetResolvedImageView(res->directLight.imageViewProxy->Id());
+    if (name == "blurredDirectLight") return g->GetResolvedImageView(res->blurredDirectLight.imageViewProxy->Id());
+    if (name == "shadowMap") return g->GetResolvedImageView(res->shadowMap.imageViewProxy->Id());
+    if (name == "indirectLight") return g->GetResolvedImageView(res->indirectLight.imageViewProxy->Id());
+    if (name == "denoisedIndirectLight") return g->GetResolvedImageView(res->denoisedIndirectLight.imageViewProxy->Id());
+    return nullptr;
+  }
+};
+
+#define LGH_TRY(body)                                                  \
+  try {                                                                \
+    body;                                                              \
+    return LGCU_OK;                                                    \
+  } catch (const std::exception &e) {                                  \
+    return setError(LGCU_ERR_CUDA, "%s", e.what());                    \
+  }
+
+extern "C" {
+
+const char *lgh_last_error(void) { return g_error; }
+
+lgh_renderer *lgh_create(uint32_t width, uint32_t height, void *stream) {
+  try {
+    if (width == 0 || height == 0) {
+      setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_create: %ux%u", width, height);
+      return nullptr;
+    }
+    std::unique_ptr<lgh_renderer> r(new lgh_renderer());
+    r->width = width;
+    r->height = height;
+    if (stream) {
+      r->stream = static_cast<cudaStream_t>(stream);
+    } else {
+      CudaCheck(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+      r->ownsStream = true;
+    }
+    r->core.reset(new Core(r->stream));
+    r->renderer.reset(new SSVGIRenderer(r->core.get()));
+    r->renderer->RecreateSwapchainResources(vk::Extent2D(width, height), 1); // main.cpp:197-205
+    r->fragments.reset(new Buffer(size_t(r->fragmentPitch()) * height));
+    r->swapchainImage.reset(new ImageData(vk::Format::eB8G8R8A8Srgb, glm::uvec2(width, height), 1)); // LV/Swapchain.h:108
+    r->swapchainView.reset(new ImageView(r->swapchainImage.get(), 0, 1));
+    r->swapchainProxy = r->core->GetRenderGraph()->AddExternalImageView(r->swapchainView.get(), ImageUsageTypes::Present); // LV/PresentQueue.h:106-110
+    return r.release();
+  } catch (const std::exception &e) {
+    setError(LGCU_ERR_CUDA, "lgh_create: %s", e.what());
+    return nullptr;
+  }
+}
+
+void lgh_destroy(lgh_renderer *r) {
+  if (!r) return;
+  cudaStreamSynchronize(r->stream);
+  if (r->graphExec) cudaGraphExecDestroy(r->graphExec);
+  if (r->graph) cudaGraphDestroy(r->graph);
+  r->scene.reset();
+  r->swapchainProxy.Reset();
+  r->renderer.reset();
+  r->core.reset();
+  if (r->ownsStream) cudaStreamDestroy(r->stream);
+  delete r;
+}
+
+int lgh_set_camera(lgh_renderer *r, const float camPos[3], float camVertAngle, float camHorAngle, const float lightPos[3], float lightVertAngle,
+                   float lightHorAngle) {
+  if (!r || !camPos || !lightPos) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_set_camera: null argument");
+  r->camera.pos = vec3{camPos[0], camPos[1], camPos[2]};
+  r->camera.vertAngle = camVertAngle;
+  r->camera.horAngle = camHorAngle;
+  r->light.pos = vec3{lightPos[0], lightPos[1], lightPos[2]};
+  r->light.vertAngle = lightVertAngle;
+  r->light.horAngle = lightHorAngle;
+  return LGCU_OK;
+}
+
+int lgh_upload_fragments(lgh_renderer *r, const lgcu_fragment *hostFragments, uint64_t hostPitchBytes, uint32_t rowBegin, uint32_t rowEnd) {
+  if (!r || !hostFragments || rowEnd > r->height || rowBegin > rowEnd || hostPitchBytes < r->fragmentPitch())
+    return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_fragments: bad arguments");
+  LGH_TRY({
+    const uint64_t pitch = r->fragmentPitch();
+    uint8_t *dst = static_cast<uint8_t *>(r->fragments->GetHandle()) + pitch * rowBegin;
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(hostFragments) + hostPitchBytes * rowBegin;
+    if (hostPitchBytes == pitch)
+      CudaCheck(cudaMemcpyAsync(dst, src, pitch * (rowEnd - rowBegin), cudaMemcpyHostToDevice, r->stream), "upload fragments");
+    else
+      CudaCheck(cudaMemcpy2DAsync(dst, pitch, src, hostPitchBytes, pitch, rowEnd - rowBegin, cudaMemcpyHostToDevice, r->stream), "upload fragments");
+  })
+}
+
+int lgh_upload_objects(lgh_renderer *r, const lgcu_draw_call_data *hostObjects, uint32_t count) {
+  if (!r || (!hostObjects && count)) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_objects: null argument");
+  LGH_TRY({
+    r->ensureScene();
+    if (count > r->objectCapacity) throw std::runtime_error("lgh_upload_objects: more than 4096 draw calls");
+    CudaCheck(cudaMemcpyAsync(r->objects->GetHandle(), hostObjects, size_t(count) * sizeof(lgcu_draw_call_data), cudaMemcpyHostToDevice, r->stream), "upload objects");
+    r->objectCount = count;
+  })
+}
+
+int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t size) {
+  if (!r || !hostDepth || size != 1024) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_light_depth: the shadow map is 1024x1024 (SSVGIRenderer.h:402)");
+  LGH_TRY({
+    r->ensureScene();
+    CudaCheck(cudaMemcpyAsync(r->lightDepth->GetHandle(), hostDepth, size_t(size) * size * 4, cudaMemcpyHostToDevice, r->stream), "upload light depth");
+  })
+}
+
+int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_render_frame: null renderer");
+  LGH_TRY(r->declareAndExecute(mode, denoiserRadius, giFlags, rows, profile != 0))
+}
+
+int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_capture_frame: null renderer");
+  try {
+    if (r->graphExec) {
+      cudaGraphExecDestroy(r->graphExec);
+      r->graphExec = nullptr;
+    }
+    if (r->graph) {
+      cudaGraphDestroy(r->graph);
+      r->graph = nullptr;
+    }
+    CudaCheck(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    try {
+      r->declareAndExecute(mode, denoiserRadius, giFlags, rows, false);
+    } catch (...) {
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(r->stream, &dead);
+      if (dead) cudaGraphDestroy(dead);
+      throw;
+    }
+    CudaCheck(cudaStreamEndCapture(r->stream, &r->graph), "cudaStreamEndCapture");
+    CudaCheck(cudaGraphInstantiate(&r->graphExec, r->graph, 0), "cudaGraphInstantiate");
+    size_t nodes = 0;
+    CudaCheck(cudaGraphGetNodes(r->graph, nullptr, &nodes), "cudaGraphGetNodes");
+    std::vector<cudaGraphNode_t> list(nodes);
+    if (nodes) CudaCheck(cudaGraphGetNodes(r->graph, list.data(), &nodes), "cudaGraphGetNodes");
+    r->graphKernels = 0;
+    for (size_t i = 0; i < nodes; i++) {
+      cudaGraphNodeType type;
+      CudaCheck(cudaGraphNodeGetType(list[i], &type), "cudaGraphNodeGetType");
+      if (type == cudaGraphNodeTypeKernel) r->graphKernels++;
+    }
+    return LGCU_OK;
+  } catch (const std::exception &e) {
+    return setError(LGCU_ERR_CUDA, "lgh_capture_frame: %s", e.what());
+  }
+}
+
+int lgh_replay_frame(lgh_renderer *r) {
+  if (!r || !r->graphExec) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_replay_frame: no captured frame");
+  LGH_TRY(CudaCheck(cudaGraphLaunch(r->graphExec, r->stream), "cudaGraphLaunch"))
+}
+
+int lgh_captured_kernel_count(lgh_renderer *r) { return r ? r->graphKernels : 0; }
+int lgh_last_pass_count(lgh_renderer *r) { return r ? r->lastPassCount : 0; }
+
+int lgh_image_desc(lgh_renderer *r, const char *name, lgcu_image *out) {
+  if (!r || !name || !out) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_image_desc: null argument");
+  ImageView *view = r->findImage(name);
+  if (!view) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_image_desc: unknown or unresolved image '%s' (render a frame first)", name);
+  *out = *view->GetDesc();
+  return LGCU_OK;
+}
+
+int lgh_download_image(lgh_renderer *r, const char *name, uint32_t level, void *host, uint64_t hostPitchBytes, uint32_t rowBegin, uint32_t rowEnd) {
+  if (!r || !name || !host) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_download_image: null argument");
+  ImageView *view = r->findImage(name);
+  if (!view) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_download_image: unknown or unresolved image '%s'", name);
+  const lgcu_image *d = view->GetDesc();
+  if (level >= d->imageMipCount) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_download_image: level %u", level);
+  const uint32_t w = d->width >> level, h = d->height >> level;
+  const uint64_t rowBytes = uint64_t(w) * lgcu_format_texel_size(d->format);
+  if (rowEnd > h || rowBegin > rowEnd || hostPitchBytes < rowBytes) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_download_image: rows / pitch");
+  LGH_TRY({
+    const uint8_t *src = static_cast<const uint8_t *>(d->base) + d->levelOffset[level] + uint64_t(d->levelPitch[level]) * rowBegin;
+    uint8_t *dst = static_cast<uint8_t *>(host) + hostPitchBytes * rowBegin;
+    if (rowEnd > rowBegin)
+      CudaCheck(cudaMemcpy2DAsync(dst, hostPitchBytes, src, d->levelPitch[level], rowBytes, rowEnd - rowBegin, cudaMemcpyDeviceToHost, r->stream), "download image");
+  })
+}
+
+int lgh_sync(lgh_renderer *r) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_sync: null renderer");
+  LGH_TRY(CudaCheck(cudaStreamSynchronize(r->stream), "cudaStreamSynchronize"))
+}
+
+int lgh_get_profile(lgh_renderer *r, char *nameBuf, uint64_t nameBufBytes, float *ms, uint32_t maxPasses) {
+  if (!r || !r->profiled) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_get_profile: the last frame was not profiled");
+  std::vector<ProfilerTask> tasks = r->gpuProfiler.GatherTasks();
+  std::string names;
+  uint32_t n = 0;
+  for (const ProfilerTask &t : tasks) {
+    if (n >= maxPasses) break;
+    if (ms) ms[n] = float(t.GetLength() * 1e3);
+    names += t.name;
+    names += '\n';
+    n++;
+  }
+  if (nameBuf && nameBufBytes) {
+    std::strncpy(nameBuf, names.c_str(), nameBufBytes - 1);
+    nameBuf[nameBufBytes - 1] = 0;
+  }
+  return int(n);
+}
+
+uint64_t lgh_allocated_bytes(lgh_renderer *r) { return r ? r->core->GetRenderGraph()->GetAllocatedBytes() : 0; }
+
+} // extern "C"

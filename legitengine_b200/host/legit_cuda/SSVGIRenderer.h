@@ -1,0 +1,378 @@
+// SSVGIRenderer.h — the reference's SSVGI renderer (src/Render/Renderers/SSVGIRenderer.h) on legit_cuda::RenderGraph.
+//
+// Same screen images (ViewportResources, :391-419), same UBO structs (include/lgcu.h mirrors :33-38, :422-519), same
+// pass list in the same AddPass order with the same attachments / inputs / render areas / profiler names and colours
+// (:63-342). Each record lambda fills its parameter block through the ShaderMemoryPool like the reference and then
+// calls one lgcu_* entry point where the reference binds a pipeline + descriptor set and draws a full-screen quad.
+//
+// What differs, and why:
+//  * Scene. The reference rasterises meshes (Scene::IterateObjects, :84-102, :138-156). Rasterisation is outside the
+//    hot path, so the scene arrives already rasterised: a per-pixel fragment buffer, the
+//    per-draw-call constants and the light's depth map. "ShadowPass" copies that depth map into the shadowMap image;
+//    "GBufferPass" runs the fragment stage (lgcu_gbuffer_resolve) over the fragment buffer.
+//  * FrameOptions::mode == Fused replaces groups of passes by the fused entry points (K1+K2, mip+blur chain, K6+K7):
+//    identical images, fewer trips through HBM. PassGranular is the 1:1 pass list (47 passes incl. shadow).
+//  * The debug overlay (DebugRenderer, :344-350) is out of scope.
+#pragma once
+
+#include <memory>
+
+#include "BlurBuilder.h"
+#include "Camera.h"
+#include "MipBuilder.h"
+
+namespace legit_cuda {
+
+// Mirrors legit::InFlightQueue::FrameInfo (LV/PresentQueue.h:71-80): what BeginFrame hands to RenderFrame.
+struct FrameInfo {
+  ShaderMemoryPool *memoryPool = nullptr;
+  RenderGraph::ImageViewProxyId swapchainImageViewProxyId;
+};
+
+// The rasterised scene (see header comment). Buffers are device memory registered as external buffers.
+struct Scene {
+  Scene(RenderGraph *graph, Buffer *fragments_, uint64_t fragmentPitch_, Buffer *objects_, uint32_t objectsCount_, Buffer *lightDepth_, uint32_t lightDepthSize_)
+      : fragments(fragments_), objects(objects_), lightDepth(lightDepth_), fragmentPitch(fragmentPitch_), objectsCount(objectsCount_), lightDepthSize(lightDepthSize_) {
+    fragmentsProxy = graph->AddExternalBuffer(fragments);
+    objectsProxy = graph->AddExternalBuffer(objects);
+    lightDepthProxy = graph->AddExternalBuffer(lightDepth);
+  }
+  Buffer *fragments, *objects, *lightDepth;
+  uint64_t fragmentPitch;
+  uint32_t objectsCount, lightDepthSize;
+  RenderGraph::BufferProxyUnique fragmentsProxy, objectsProxy, lightDepthProxy;
+};
+
+struct FrameOptions {
+  enum struct Mode { PassGranular, Fused };
+  Mode mode = Mode::Fused;
+  int denoiserRadius = 0;               // key 'A' held -> 2 in the reference (:288)
+  uint32_t giFlags = LGCU_GI_DEFAULT;   // LGCU_GI_STRICT selects the shader-order parity kernel
+  bool useRows = false;                 // multi-GPU strip: only rows [rows.y0, rows.y1) of the frame are produced
+  lgcu_rows rows{0, 0};
+};
+
+class SSVGIRenderer {
+public:
+  explicit SSVGIRenderer(Core *_core)
+      : mipBuilder(_core), blurBuilder(_core), screenspaceSampler(SamplerAddressMode::eClampToEdge, Filter::eLinear, SamplerMipmapMode::eLinear),
+        shadowmapSampler(SamplerAddressMode::eClampToEdge, Filter::eLinear, SamplerMipmapMode::eNearest, true), core(_core) {}
+
+  void RecreateSceneResources(Scene *) {}
+  void RecreateSwapchainResources(vk::Extent2D _viewportExtent, size_t /*inFlightFramesCount*/) {
+    viewportExtent = _viewportExtent;
+    viewportResources.reset(new ViewportResources(core->GetRenderGraph(), glm::uvec2(viewportExtent.width, viewportExtent.height)));
+  }
+
+  void RenderFrame(const FrameInfo &frameInfo, const Camera &camera, const Camera &light, Scene *scene, const FrameOptions &options = FrameOptions()) {
+    struct PassData {
+      ShaderMemoryPool *memoryPool;
+      lgcu_mat4 viewMatrix, projMatrix, lightViewMatrix, lightProjMatrix;
+      Scene *scene;
+      const lgcu_rows *rows;
+      lgcu_rows rowsStorage;
+    } passData;
+    passData.memoryPool = frameInfo.memoryPool;
+    passData.scene = scene;
+    const FrameMatrices frame = MakeFrameMatrices(camera, light, viewportExtent.width, viewportExtent.height); // :54-59
+    passData.viewMatrix = frame.viewMatrix;
+    passData.projMatrix = frame.projMatrix;
+    passData.lightViewMatrix = frame.lightViewMatrix;
+    passData.lightProjMatrix = frame.lightProjMatrix;
+    passData.rowsStorage = options.rows;
+    RenderGraph *graph = core->GetRenderGraph();
+    ViewportResources *res = viewportResources.get();
+    const bool useRows = options.useRows;
+    auto rowsOf = [useRows](const PassData &pd) -> const lgcu_rows * { return useRows ? &pd.rowsStorage : nullptr; };
+
+    // rendering shadow map (:61-104) — the light's depth arrives rasterised with the scene
+    vk::Extent2D shadowMapExtent(res->shadowMap.baseSize.x, res->shadowMap.baseSize.y);
+    graph->AddPass(RenderGraph::RenderPassDesc()
+                       .SetDepthAttachment(res->shadowMap.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
+                       .SetStorageBuffers({scene->lightDepthProxy->Id()})
+                       .SetRenderAreaExtent(shadowMapExtent)
+                       .SetProfilerInfo(Colors::amethyst, "ShadowPass")
+                       .SetRecordFunc([passData](RenderGraph::RenderPassContext passContext) {
+                         ImageView *shadowMap = passContext.GetDepthAttachment();
+                         const uint32_t size = passData.scene->lightDepthSize;
+                         if (shadowMap->GetImageData()->GetMipSize(0).x != size) throw std::runtime_error("ShadowPass: light depth size != shadow map size");
+                         CudaCheck(cudaMemcpy2DAsync(shadowMap->GetImageData()->GetLevelPointer(0), shadowMap->GetImageData()->GetLevelPitch(0),
+                                                     passContext.GetBuffer(passData.scene->lightDepthProxy->Id())->GetHandle(), size_t(size) * 4, size_t(size) * 4, size,
+                                                     cudaMemcpyDeviceToDevice, passContext.GetStream()),
+                                   "ShadowPass copy");
+                       }));
+
+    auto fillGBufferData = [](const PassData &pd) {
+      pd.memoryPool->BeginSet();
+      auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_gbuffer_builder_data>("GBufferBuilderData");
+      shaderDataBuffer->time = 0.0f;
+      shaderDataBuffer->projMatrix = pd.projMatrix;
+      shaderDataBuffer->viewMatrix = pd.viewMatrix;
+      pd.memoryPool->EndSet();
+      return shaderDataBuffer;
+    };
+    auto fillLightData = [](const PassData &pd) {
+      pd.memoryPool->BeginSet();
+      auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_direct_lighting_data>("DirectLightingData");
+      shaderDataBuffer->viewMatrix = pd.viewMatrix;
+      shaderDataBuffer->projMatrix = pd.projMatrix;
+      shaderDataBuffer->lightViewMatrix = pd.lightViewMatrix;
+      shaderDataBuffer->lightProjMatrix = pd.lightProjMatrix;
+      shaderDataBuffer->time = 0.0f;
+      pd.memoryPool->EndSet();
+      return shaderDataBuffer;
+    };
+    auto clearOf = [](RenderGraph::RenderPassContext &ctx) {
+      lgcu_clear_values clear;
+      const vk::ClearValue color = ctx.GetColorClearValue(0);
+      for (int i = 0; i < 4; i++) clear.color[i] = color.color.float32[size_t(i)];
+      clear.depth = ctx.GetDepthClearValue().depthStencil.depth;
+      return clear;
+    };
+
+    if (options.mode == FrameOptions::Mode::PassGranular) {
+      // rendering gbuffer (:106-158): fragment stage over the rasterised fragments
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->albedo.imageViewProxy->Id(),                  // location = 0
+                                               res->emissive.imageViewProxy->Id(),                // location = 1
+                                               res->normal.imageViewProxy->Id(),                  // location = 2
+                                               res->depthMoments.mipImageViewProxies[0]->Id()},   // location = 3
+                                              vk::AttachmentLoadOp::eClear)
+                         .SetDepthAttachment(res->depthStencil.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
+                         .SetStorageBuffers({scene->fragmentsProxy->Id(), scene->objectsProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::belizeHole, "GBufferPass")
+                         .SetRecordFunc([passData, fillGBufferData, clearOf, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillGBufferData(passData);
+                           const lgcu_clear_values clear = clearOf(passContext);
+                           Scene *sc = passData.scene;
+                           LgcuCheck(lgcu_gbuffer_resolve(shaderDataBuffer, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
+                                                          sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
+                                                          sc->fragmentPitch, &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
+                                                          passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(),
+                                                          passContext.GetDepthAttachment()->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "GBufferPass");
+                         }));
+
+      // applying direct lighting (:160-205)
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->directLight.mipImageViewProxies[0]->Id()})
+                         .SetInputImages({res->albedo.imageViewProxy->Id(), res->emissive.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                                          res->depthStencil.imageViewProxy->Id(), res->shadowMap.imageViewProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::orange, "LightPass")
+                         .SetRecordFunc([this, passData, fillLightData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillLightData(passData);
+                           ViewportResources *r = this->viewportResources.get();
+                           LgcuCheck(lgcu_direct_light(shaderDataBuffer, passContext.GetImageView(r->albedo.imageViewProxy->Id())->GetDesc(),  // "albedoSampler"
+                                                       passContext.GetImageView(r->emissive.imageViewProxy->Id())->GetDesc(),                   // "emissiveSampler"
+                                                       passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),                     // "normalSampler"
+                                                       passContext.GetImageView(r->depthStencil.imageViewProxy->Id())->GetDesc(),               // "depthStencilSampler"
+                                                       passContext.GetImageView(r->shadowMap.imageViewProxy->Id())->GetDesc(),                  // "shadowmapSampler"
+                                                       passContext.GetColorAttachment(0)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "LightPass");
+                         }));
+
+      // :207-221 — with a row strip the per-level passes would need per-level row ranges; strips always use Fused
+      if (useRows) throw std::runtime_error("SSVGIRenderer: row strips require FrameOptions::Mode::Fused");
+      mipBuilder.BuildMips(graph, frameInfo.memoryPool, res->directLight);
+      mipBuilder.BuildMips(graph, frameInfo.memoryPool, res->depthMoments);
+      for (uint32_t mipLevel = 0; mipLevel < res->blurredDirectLight.mipImageViewProxies.size(); mipLevel++)
+        blurBuilder.ApplyBlur(graph, frameInfo.memoryPool, res->directLight.mipImageViewProxies[mipLevel]->Id(),
+                              res->blurredDirectLight.mipImageViewProxies[mipLevel]->Id(), mipLevel == 0 ? 0 : 2);
+      for (uint32_t mipLevel = 0; mipLevel < res->blurredDirectLight.mipImageViewProxies.size(); mipLevel++)
+        blurBuilder.ApplyBlur(graph, frameInfo.memoryPool, res->depthMoments.mipImageViewProxies[mipLevel]->Id(),
+                              res->blurredDepthMoments.mipImageViewProxies[mipLevel]->Id(), mipLevel == 0 ? 0 : 2);
+    } else {
+      // K1 + K2 fused: everything GBufferPass and LightPass write, from one read of the fragments
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->albedo.imageViewProxy->Id(), res->emissive.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                                               res->depthMoments.mipImageViewProxies[0]->Id(), res->directLight.mipImageViewProxies[0]->Id()},
+                                              vk::AttachmentLoadOp::eClear)
+                         .SetDepthAttachment(res->depthStencil.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
+                         .SetInputImages({res->shadowMap.imageViewProxy->Id()})
+                         .SetStorageBuffers({scene->fragmentsProxy->Id(), scene->objectsProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::belizeHole, "GBufferLightPass")
+                         .SetRecordFunc([this, passData, fillGBufferData, fillLightData, clearOf, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto gbufferData = fillGBufferData(passData);
+                           auto lightData = fillLightData(passData);
+                           const lgcu_clear_values clear = clearOf(passContext);
+                           Scene *sc = passData.scene;
+                           LgcuCheck(lgcu_gbuffer_direct_light(
+                                         gbufferData, lightData, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
+                                         sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()), sc->fragmentPitch,
+                                         &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
+                                         passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(), passContext.GetDepthAttachment()->GetDesc(),
+                                         passContext.GetImageView(this->viewportResources->shadowMap.imageViewProxy->Id())->GetDesc(),
+                                         passContext.GetColorAttachment(4)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "GBufferLightPass");
+                         }));
+      // K3 + K4 fused per chain (BuildMips + ten ApplyBlur, :207-221)
+      auto addChain = [&](const MippedProxy &chain, const MippedProxy &blurred) {
+        auto chainId = chain.imageViewProxy->Id(), blurredId = blurred.imageViewProxy->Id();
+        graph->AddPass(RenderGraph::RenderPassDesc()
+                           .SetStorageImages({chainId, blurredId})
+                           .SetRenderAreaExtent(viewportExtent)
+                           .SetProfilerInfo(Colors::nephritis, "MipBlurChainPass")
+                           .SetRecordFunc([passData, chainId, blurredId, rowsOf](RenderGraph::RenderPassContext passContext) {
+                             LgcuCheck(lgcu_mip_blur_chain(passContext.GetImageView(chainId)->GetDesc(), passContext.GetImageView(blurredId)->GetDesc(), 2, rowsOf(passData),
+                                                           passContext.GetStream()),
+                                       "MipBlurChainPass");
+                           }));
+      };
+      addChain(res->directLight, res->blurredDirectLight);
+      addChain(res->depthMoments, res->blurredDepthMoments);
+    }
+
+    // calculating indirect lighting (:223-263)
+    const uint32_t giFlags = options.giFlags;
+    graph->AddPass(RenderGraph::RenderPassDesc()
+                       .SetColorAttachments({res->indirectLight.imageViewProxy->Id()})
+                       .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                                        res->depthStencil.imageViewProxy->Id()})
+                       .SetRenderAreaExtent(viewportExtent)
+                       .SetProfilerInfo(Colors::sunFlower, "IndirectLightPass")
+                       .SetRecordFunc([this, passData, giFlags, rowsOf](RenderGraph::RenderPassContext passContext) {
+                         passData.memoryPool->BeginSet();
+                         auto shaderDataBuffer = passData.memoryPool->GetUniformBufferData<lgcu_indirect_lighting_data>("IndirectLightingData");
+                         shaderDataBuffer->viewMatrix = passData.viewMatrix;
+                         shaderDataBuffer->projMatrix = passData.projMatrix;
+                         shaderDataBuffer->viewportExtent[0] = float(this->viewportExtent.width);
+                         shaderDataBuffer->viewportExtent[1] = float(this->viewportExtent.height);
+                         shaderDataBuffer->viewportExtent[2] = shaderDataBuffer->viewportExtent[3] = 0.0f;
+                         passData.memoryPool->EndSet();
+                         ViewportResources *r = this->viewportResources.get();
+                         LgcuCheck(lgcu_gi_gather(shaderDataBuffer, passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(), // "blurredDirectLightSampler"
+                                                  passContext.GetImageView(r->blurredDepthMoments.imageViewProxy->Id())->GetDesc(),                // "blurredDepthMomentsSampler"
+                                                  passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),                             // "normalSampler"
+                                                  passContext.GetImageView(r->depthStencil.imageViewProxy->Id())->GetDesc(),                       // "depthStencilSampler"
+                                                  passContext.GetColorAttachment(0)->GetDesc(), giFlags, rowsOf(passData), passContext.GetStream()),
+                                   "IndirectLightPass");
+                       }));
+
+    const int denoiserRadius = options.denoiserRadius;
+    auto fillDenoiserData = [this, denoiserRadius](const PassData &pd) {
+      pd.memoryPool->BeginSet();
+      auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_denoiser_data>("DenoiserData");
+      shaderDataBuffer->viewMatrix = pd.viewMatrix;
+      shaderDataBuffer->projMatrix = pd.projMatrix;
+      shaderDataBuffer->viewportExtent[0] = float(this->viewportExtent.width);
+      shaderDataBuffer->viewportExtent[1] = float(this->viewportExtent.height);
+      shaderDataBuffer->viewportExtent[2] = shaderDataBuffer->viewportExtent[3] = 0.0f;
+      shaderDataBuffer->radius = denoiserRadius;
+      pd.memoryPool->EndSet();
+      return shaderDataBuffer;
+    };
+    auto fillFinalData = [](const PassData &pd) {
+      pd.memoryPool->BeginSet();
+      auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_final_gatherer_data>("FinalGathererData");
+      shaderDataBuffer->viewMatrix = pd.viewMatrix;
+      shaderDataBuffer->projMatrix = pd.projMatrix;
+      pd.memoryPool->EndSet();
+      return shaderDataBuffer;
+    };
+
+    if (options.mode == FrameOptions::Mode::PassGranular) {
+      // denoising indirect lighting (:265-302)
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->denoisedIndirectLight.imageViewProxy->Id()})
+                         .SetInputImages({res->depthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(), res->indirectLight.imageViewProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::greenSea, "DenoiserPass")
+                         .SetRecordFunc([this, passData, fillDenoiserData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillDenoiserData(passData);
+                           ViewportResources *r = this->viewportResources.get();
+                           LgcuCheck(lgcu_denoise(shaderDataBuffer, passContext.GetImageView(r->indirectLight.imageViewProxy->Id())->GetDesc(), // "noisySampler"
+                                                  passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),                          // "normalSampler"
+                                                  passContext.GetImageView(r->depthMoments.imageViewProxy->Id())->GetDesc(),                    // "depthStencilSampler" (:293)
+                                                  passContext.GetColorAttachment(0)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "DenoiserPass");
+                         }));
+      // final gathering (:304-342)
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({frameInfo.swapchainImageViewProxyId})
+                         .SetInputImages({res->directLight.imageViewProxy->Id(), res->blurredDirectLight.imageViewProxy->Id(), res->albedo.imageViewProxy->Id(),
+                                          res->denoisedIndirectLight.imageViewProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::pomegranate, "GatheringPass")
+                         .SetRecordFunc([this, passData, fillFinalData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillFinalData(passData);
+                           ViewportResources *r = this->viewportResources.get();
+                           LgcuCheck(lgcu_final_gather(shaderDataBuffer, passContext.GetImageView(r->directLight.imageViewProxy->Id())->GetDesc(),  // "directLightSampler"
+                                                       passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(),             // "blurredDirectLightSampler"
+                                                       passContext.GetImageView(r->albedo.imageViewProxy->Id())->GetDesc(),                         // "albedoSampler"
+                                                       passContext.GetImageView(r->denoisedIndirectLight.imageViewProxy->Id())->GetDesc(),          // "indirectLightSampler"
+                                                       passContext.GetColorAttachment(0)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "GatheringPass");
+                         }));
+    } else {
+      // K6 + K7 fused
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->denoisedIndirectLight.imageViewProxy->Id(), frameInfo.swapchainImageViewProxyId})
+                         .SetInputImages({res->depthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(), res->indirectLight.imageViewProxy->Id(),
+                                          res->directLight.imageViewProxy->Id(), res->blurredDirectLight.imageViewProxy->Id(), res->albedo.imageViewProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::pomegranate, "DenoiseGatheringPass")
+                         .SetRecordFunc([this, passData, fillDenoiserData, fillFinalData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto denoiserData = fillDenoiserData(passData);
+                           auto finalData = fillFinalData(passData);
+                           ViewportResources *r = this->viewportResources.get();
+                           LgcuCheck(lgcu_denoise_final_gather(denoiserData, finalData, passContext.GetImageView(r->indirectLight.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetImageView(r->depthMoments.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetColorAttachment(0)->GetDesc(),
+                                                               passContext.GetImageView(r->directLight.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetImageView(r->albedo.imageViewProxy->Id())->GetDesc(),
+                                                               passContext.GetColorAttachment(1)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "DenoiseGatheringPass");
+                         }));
+    }
+  }
+
+  void ReloadShaders() {
+    mipBuilder.ReloadShaders();
+    blurBuilder.ReloadShaders();
+  }
+
+  // :391-419
+  struct ViewportResources {
+    ViewportResources(RenderGraph *renderGraph, glm::uvec2 screenSize)
+        : albedo(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          emissive(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          normal(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          depthMoments(renderGraph, vk::Format::eR32G32Sfloat, screenSize, colorImageUsage),
+          blurredDepthMoments(renderGraph, vk::Format::eR32G32Sfloat, screenSize, colorImageUsage),
+          depthStencil(renderGraph, vk::Format::eD32Sfloat, screenSize, depthImageUsage),
+          directLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          blurredDirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          shadowMap(renderGraph, vk::Format::eD32Sfloat, glm::uvec2(1024, 1024), depthImageUsage),
+          indirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          denoisedIndirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage) {}
+    UnmippedProxy albedo;
+    UnmippedProxy emissive;
+    UnmippedProxy normal;
+    MippedProxy depthMoments;
+    MippedProxy blurredDepthMoments;
+    UnmippedProxy depthStencil;
+    MippedProxy directLight;
+    MippedProxy blurredDirectLight;
+    UnmippedProxy shadowMap;
+    UnmippedProxy indirectLight;
+    UnmippedProxy denoisedIndirectLight;
+  };
+  ViewportResources *GetViewportResources() { return viewportResources.get(); }
+  vk::Extent2D GetViewportExtent() const { return viewportExtent; }
+
+private:
+  std::unique_ptr<ViewportResources> viewportResources;
+  vk::Extent2D viewportExtent;
+  MipBuilder mipBuilder;
+  BlurBuilder blurBuilder;
+  Sampler screenspaceSampler;
+  Sampler shadowmapSampler;
+  Core *core;
+};
+
+} // namespace legit_cuda
