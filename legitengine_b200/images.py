@@ -113,7 +113,7 @@ class HostImage(_ImageBase):
         fmt = self.format
         w, h = self.level_size(level)
         if fmt == abi.FORMAT_R16G16B16A16_SFLOAT:
-            raw = np.asarray(values, dtype=np.float32).astype(np.float16).reshape(h, w, 4).view(np.uint8)
+            raw = np.ascontiguousarray(np.asarray(values, dtype=np.float32).astype(np.float16).reshape(h, w, 4)).view(np.uint8)
         elif fmt in (abi.FORMAT_R32G32_SFLOAT, abi.FORMAT_R32G32B32A32_SFLOAT, abi.FORMAT_D32_SFLOAT):
             ch = {abi.FORMAT_R32G32_SFLOAT: 2, abi.FORMAT_R32G32B32A32_SFLOAT: 4, abi.FORMAT_D32_SFLOAT: 1}[fmt]
             raw = np.ascontiguousarray(np.asarray(values, dtype=np.float32).reshape(h, w, ch)).view(np.uint8)

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures of the SSVGI path FROM THE REFERENCE ARM (oracle/_ref/libref_spirv.so: the
+reference's own shipped SPIR-V passes run through its vendored SPIRV-Cross C++ backend and GLM, built from
+/root/reference by oracle/Makefile). Run in the development container only (the reference tree does not exist on the
+GPU box):
+
+    python tests/golden/make_golden.py
+
+Each fixture is one small frame: the INPUTS of the path (fragment buffer, per-draw-call table, light depth map, the
+four frame matrices) and every image the reference passes produce from them, all levels, as raw storage bytes.
+The reference ships no golden vectors of its own for this path, so these — outputs of the reference's
+arithmetic itself — are the pins: tests check the C port, and on the GPU the CUDA passes, against them.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+
+from legitengine_b200 import abi, images, passes, scene  # noqa: E402
+from oracle import loader  # noqa: E402
+
+# name: (seed, W, H, boxes, denoise radius, shadow-map size)
+FIXTURES = {
+    "ssvgi_64x36_s3_r0": (3, 64, 36, 24, 0, 128),
+    "ssvgi_50x29_s5_r2": (5, 50, 29, 16, 2, 64),   # ragged size: odd trailing rows/columns dropped by the mip chain
+    "ssvgi_96x64_s9_r0": (9, 96, 64, 64, 0, 256),
+}
+
+
+def main() -> None:
+    ref = loader.ref()
+    for name, (seed, W, H, boxes, radius, shadow) in FIXTURES.items():
+        sc = scene.make_scene(seed, W, H, n_boxes=boxes, shadow_size=shadow)
+        p = passes.make_params(W, H, sc.matrices, radius)
+        fi = passes.FrameImages(W, H, images.HostImage, shadow_size=shadow)
+        passes.run_pass_list(ref, fi, p, passes.upload_inputs(fi, sc))
+        out = {
+            "meta": np.array([seed, W, H, boxes, radius, shadow], dtype=np.int64),
+            "fragments": sc.fragments.view(np.uint8).reshape(H, W * 32).copy(),
+            "objects": sc.objects.view(np.uint8).reshape(-1).copy(),
+            "shadow_map": sc.shadow_map.copy(),
+            "view": sc.matrices.view, "proj": sc.matrices.proj, "light_view": sc.matrices.light_view, "light_proj": sc.matrices.light_proj,
+        }
+        for iname, img in fi.items():
+            if iname == "shadowMap":
+                continue
+            for l in range(img.mips):
+                w, h = img.level_size(l)
+                if w > 0 and h > 0:
+                    out[f"img.{iname}.{l}"] = np.ascontiguousarray(img.level_bytes(l))
+        path = HERE / f"{name}.npz"
+        np.savez_compressed(path, **out)
+        print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -75,3 +75,26 @@ def assert_close(cuda_img, ref_img, level=0, what="", max_outside_frac=1e-4, min
     assert r["outside_tol"] <= max_outside_frac * r["texels"], f"{what} level {level}: {r}"
     assert r["psnr"] >= min_psnr, f"{what} level {level}: {r}"
     return r
+
+
+# ---- committed golden fixtures (tests/golden/*.npz, generated from the reference arm by tests/golden/make_golden.py) ----
+GOLDEN_DIR = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+GOLDEN_NAMES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
+
+
+def load_golden(name: str):
+    """-> (scene, params, FrameImages on the host holding the reference arm's outputs, denoise radius)."""
+    z = np.load(GOLDEN_DIR / f"{name}.npz")
+    seed, W, Hh, boxes, radius, shadow = (int(v) for v in z["meta"])
+    m = scene.FrameMatrices(z["view"].copy(), z["proj"].copy(), z["light_view"].copy(), z["light_proj"].copy())
+    frags = np.ascontiguousarray(z["fragments"]).view(abi.FRAGMENT_DTYPE).reshape(Hh, W)
+    objs = np.ascontiguousarray(z["objects"]).view(abi.DRAW_CALL_DTYPE)
+    sc = scene.Scene(W, Hh, seed, m, frags, objs, z["shadow_map"].copy())
+    p = passes.make_params(W, Hh, m, radius)
+    fi = passes.FrameImages(W, Hh, images.HostImage, shadow_size=shadow)
+    fi.shadowMap.set_level(0, sc.shadow_map[..., None])
+    for key in z.files:
+        if key.startswith("img."):
+            _, iname, level = key.split(".")
+            getattr(fi, iname).level_bytes(int(level))[...] = z[key]
+    return sc, p, fi, radius

@@ -199,3 +199,34 @@ def test_full_frame_chained(cu):
     a = dev.swapchain.to_host().level_raw(0).astype(np.int32)
     b = ref.swapchain.level_raw(0).astype(np.int32)
     assert (np.abs(a - b) > 1).mean() < 1e-3
+
+
+@pytest.mark.parametrize("flags", [abi.GI_STRICT, abi.GI_DEFAULT], ids=["strict", "fast"])
+@pytest.mark.parametrize("name", H.GOLDEN_NAMES)
+def test_frame_vs_reference_golden_fixture(cu, name, flags):
+    """CUDA frame from the committed fixture's inputs vs the images the REFERENCE's own SPIR-V passes produced from them
+    (tests/golden/make_golden.py). Integer/index work bit-exact, radiance within the north-star tolerance."""
+    sc, p, ref, radius = H.load_golden(name)
+    dev = H.device_frame_like(ref)
+    inp = passes.upload_inputs(dev, sc)
+    passes.run_pass_list(cu, dev, p, inp, gi_flags=flags, stop_after="gather")
+    _sync()
+    levels = passes.mip_levels_built(sc.width, sc.height)
+    for iname in ("normal", "depthMoments", "depthStencil"):
+        H.assert_bit_exact(getattr(dev, iname).to_host(), getattr(ref, iname), 0, iname)
+    for l in range(levels):  # moments chain: pure exact-order fp32 -> bit-exact on every level
+        H.assert_bit_exact(dev.depthMoments.to_host(), ref.depthMoments, l, "depthMoments")
+        H.assert_bit_exact(dev.blurredDepthMoments.to_host(), ref.blurredDepthMoments, l, "blurredDepthMoments")
+    for iname in ("directLight", "blurredDirectLight"):
+        host = getattr(dev, iname).to_host()
+        for l in range(levels):
+            H.assert_close(host, getattr(ref, iname), l, iname, max_outside_frac=2e-3)
+    H.assert_close(dev.indirectLight.to_host(), ref.indirectLight, 0, "indirectLight", max_outside_frac=2e-3)
+    if radius == 0:
+        cu.denoise(C.byref(p.denoiser), _v(dev.indirectLight), _v(dev.normal), _v(dev.depthMoments), _v(dev.denoisedIndirectLight), None)
+        cu.final_gather(C.byref(p.final), _v(dev.directLight), _v(dev.blurredDirectLight), _v(dev.albedo), _v(dev.denoisedIndirectLight),
+                        _v(dev.swapchain), None)
+        _sync()
+        a = dev.swapchain.to_host().level_raw(0).astype(np.int32)
+        b = ref.swapchain.level_raw(0).astype(np.int32)
+        assert (np.abs(a - b) > 1).mean() < 2e-3
