@@ -159,6 +159,21 @@ int lgcu_gi_gather(const lgcu_indirect_lighting_data *params, const lgcu_image *
 #define LGCU_GI_DEFAULT 0u
 #define LGCU_GI_STRICT 1u /* shader-order arithmetic with libm-grade sin/cos/atan/pow/log (parity variant) */
 
+/* K5 with the quad-packed depth pyramid (a private acceleration structure of this library):
+ *   bytes   = lgcu_gather_scratch_bytes(width, height, mips)      size of the scratch buffer for a pyramid of that shape
+ *   lgcu_gi_gather_pack(...)    builds the scratch from blurredDepthMoments (after the blur passes, before the gather)
+ *   lgcu_gi_gather_packed(...)  the same pass as lgcu_gi_gather(LGCU_GI_DEFAULT), reading depth through the scratch
+ * scratch is DEVICE memory owned by the caller (16-byte aligned); the image arguments are those of lgcu_gi_gather. With a
+ * row strip, pack rebuilds the rows the strip's march can reach. */
+uint64_t lgcu_gather_scratch_bytes(uint32_t width, uint32_t height, uint32_t mips);
+int lgcu_gi_gather_pack(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight,
+                        const lgcu_image *blurredDepthMoments, const lgcu_image *normal, const lgcu_image *depthStencil,
+                        const lgcu_image *indirectLight, void *scratch, uint64_t scratchBytes, const lgcu_rows *rows, void *stream);
+int lgcu_gi_gather_packed(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight,
+                          const lgcu_image *blurredDepthMoments, const lgcu_image *normal, const lgcu_image *depthStencil,
+                          const lgcu_image *indirectLight, const void *scratch, uint64_t scratchBytes, const lgcu_rows *rows,
+                          void *stream);
+
 /* K6 "DenoiserPass": SH/Common/denoiser.frag:72-185, pass SSVGIRenderer.h:266-302.
  * `depthMoments` is what the reference binds to the shader's depthStencilSampler (SSVGIRenderer.h:293). */
 int lgcu_denoise(const lgcu_denoiser_data *params, const lgcu_image *noisy, const lgcu_image *normal,

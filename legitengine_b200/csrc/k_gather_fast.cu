@@ -1,24 +1,30 @@
 // k_gather_fast.cu — screen-space GI gather (K5), throughput variant for sm_100a.
 //
-// Same function as SH/SSVGI/indirectLighting.frag:114-272 (see k_gather_strict.cu for the line-by-line form), reorganised
-// around what the hardware is short of. The pass is FP32-issue / L1 bound (≈25 pyramid samples per pixel),
-// so the design removes instructions, not bytes:
+// Same function as SH/SSVGI/indirectLighting.frag:114-272 (k_gather_strict.cu is the line-by-line form). The pass is bound by
+// FP32 issue slots and the LSU, not by HBM (≈25 trilinear pyramid samples per pixel), so the design removes
+// instructions and load requests, not bytes:
 //
-//  * Pattern-coherent warps. The shader's 4x4 interleaved pattern gives every pixel with the same (x&3, y&3) the same
-//    march directions, step offsets and LODs. A CTA owns a 32x32 pixel tile and warp w processes the 64 pixels of
-//    pattern index w (2 per lane), so direction / offset / level / mip geometry are warp-uniform constant-bank operands,
-//    the level branch is uniform, and at LOD >= 2 the lanes of a warp read adjacent texels.
-//  * No transcendental per sample. pow/log (step offset, LOD, iteration count) come from the host tables shared with the
-//    strict kernel (bit-identical level selection). Miss samples are rejected with a half-plane + cross-product test
-//    instead of atan; sin(2h)/cos(2h) of ComputeHorizonContribution are evaluated algebraically from the horizon vector
-//    (x,y): cos2h = (x²-y²)/(x²+y²), sin2h = 2xy/(x²+y²). atan2f runs on hits only (the 2·maxH - 2·h term needs the angle).
-//  * The per-sample unprojection collapses to a few FMAs: the ray through pixel s is R(s) = Ra·sx + Rb·sy + Rc (affine
-//    in pixel coordinates), along a march direction R(s) = R0 + off·Rd, and every dot product the horizon test needs is
-//    affine in `off` with per-direction constants.
+//  * Pattern-coherent CTAs. The shader's 4x4 interleaved pattern gives every pixel with the same (x&3, y&3) the same march
+//    directions, step offsets and LODs. A CTA owns a 64x64 pixel tile and walks the 16 pattern classes in a CTA-uniform loop;
+//    in each pass thread t shades pixel (4*(t&15) + ox, 4*(t>>4) + oy). Direction, step offset, LOD and mip geometry are
+//    therefore uniform-datapath operands, every level branch is uniform, and neighbouring lanes read neighbouring texels
+//    from LOD 2 upwards. The 16 passes of a CTA re-touch the same pyramid neighbourhood, which stays in L1.
+//  * No transcendental per sample: pow/log (step offset, LOD, iteration count) come from host tables shared with the strict
+//    kernel (bit-identical level selection). The per-sample unprojection collapses to FMAs: the ray through pixel s is
+//    R(s) = Ra*sx + Rb*sy + Rc (affine in pixel coordinates), so along a march direction every dot product of the horizon test
+//    is affine in the step offset with per-direction constants.
+//  * One 16-byte load per bilinear depth footprint: the march reads the quad-packed side pyramid built by packDepthQuads
+//    (per level (w+1)x(h+1) float4 = the four clamp-to-edge .r taps of the footprint whose top-left texel is (qx-1, qy-1)),
+//    so the per-sample address math is one clamp + one magic-number floor per axis and there are 2 loads per trilinear
+//    sample instead of 8. Without a scratch buffer (lgcu_gi_gather) the same kernel fetches the four taps individually.
+//  * Hits are processed inline (they are spatially coherent: a warp runs the hit body on ≈2.7 of its ≈6.4 march steps per
+//    direction with ≈70 % of the lanes active; compacting them buys nothing). A sample is rejected with a half-plane +
+//    cross-product test instead of atan; on a hit atan2 is an 8-term minimax polynomial (1.2e-7 rad) and sin(2h)/cos(2h)
+//    of ComputeHorizonContribution come algebraically from the horizon vector: cos2h = (x²-y²)/(x²+y²), sin2h = 2xy/(x²+y²).
+//    The light fetch reuses the footprint (integer taps + weights) of the depth fetch.
 //  * What is numerically delicate is kept in the shader's order: the centre position is reconstructed from the D32 depth
 //    exactly as the shader does (its fp32 cancellation noise is part of the reference result and is amplified by
 //    1/sample distance), so the two variants see the same centre.
-//  * Results are staged in shared memory and written with 16-byte coalesced stores.
 #include <cmath>
 
 #include "lgcu_kernels.h"
@@ -27,19 +33,34 @@ namespace lgcu {
 
 namespace {
 
-constexpr int kTile = 32;           // pixels per tile edge
-constexpr int kThreads = 512;       // 16 warps = 16 pattern indices
+constexpr int kTile = 64;      // pixels per tile edge
+constexpr int kThreads = 256;  // 16x16 pixels of one pattern class per pass
+constexpr int kMaxSteps = 12;  // march steps the tables hold (8 are reached for landscape viewports at any resolution)
 constexpr uint32_t F16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, D32 = LGCU_FORMAT_D32_SFLOAT;
+constexpr float kFloorMagic = 12582912.0f; // 1.5 * 2^23: x + magic (rounded down) has floor(x) in its low mantissa bits
+constexpr int kFloorMagicBits = 0x4B400000;
 
-// per-(pattern, step) and per-level constants derived on the host from GatherTables (see buildFastTables)
+struct LevelGeom { // per pyramid level
+  float scaleX, scaleY; // w_l / viewport.x, h_l / viewport.y
+  float maxX, maxY;     // w_l - 1, h_l - 1
+  int quadOfs, quadPitch; // level origin and row pitch of the quad-packed depth pyramid, in float4
+  int texOfs, texPitch;   // level origin and row pitch in 8-byte texels (both pyramids share the layout)
+  int wm1, hm1;
+  int pad0, pad1;
+};
+struct StepRow { // per (pattern, step): everything the march needs for one sample, in one uniform 112-byte row
+  float off, frac;
+  int l0, l1;
+  LevelGeom g0, g1;
+};
+struct DirEntry { // per (pattern, direction)
+  float dirX, dirY, invDirX, invDirY;
+  float rdX, rdY, rdZ, q2; // Rd = Ra*dirX + Rb*dirY, q2 = |Rd|²
+};
 struct FastTables {
-  float dirX[16][kGatherDirs], dirY[16][kGatherDirs];
-  float rd[16][kGatherDirs][3]; // Rd = Ra*dirX + Rb*dirY
-  float pixelOffset[16][kGatherMaxSteps];
-  float lodFrac[16][kGatherMaxSteps];
-  signed char lod0[16][kGatherMaxSteps], lod1[16][kGatherMaxSteps];
-  float iterThreshold[kGatherMaxSteps];
-  float levelScaleX[kMaxGatherLevels], levelScaleY[kMaxGatherLevels]; // w_l / viewport.x, h_l / viewport.y
+  StepRow row[16 * kMaxSteps];
+  DirEntry dir[16][kGatherDirs];
+  float iterThreshold[kMaxSteps];
   float ra[3], rb[3], rc[3]; // R(p) = ra*px + rb*py + rc  ∝ (far-plane point through pixel p) - cam
   float raySign;             // sign of the homogeneous w of that point: rayDir = raySign * R / |R|
   int maxSteps;
@@ -55,40 +76,64 @@ __device__ __forceinline__ float fastRsqrt(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float lerpf(float p, float q, float t) { return fmaf(q - p, t, p); }
+__device__ __forceinline__ float dotf(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 
-struct Footprint { // bilinear footprint at one level, shared by the depth and the light fetch
-  int o00, o10, o01, o11; // byte offsets / 8 (texel index) from the level base
+// atan2 for finite, not-both-zero arguments: 8-term odd minimax polynomial on [0,1] (max error 1.2e-7 rad in fp32)
+__device__ __forceinline__ float atan2Poly(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mn = fminf(ax, ay), mxv = fmaxf(ax, ay);
+  const float t = mn * fastRcp(fmaxf(mxv, 1e-37f));
+  const float s = t * t;
+  float p = -0.004054398275911808f;
+  p = fmaf(p, s, 0.021862303838133812f);
+  p = fmaf(p, s, -0.055911313742399216f);
+  p = fmaf(p, s, 0.09642116725444794f);
+  p = fmaf(p, s, -0.13908594846725464f);
+  p = fmaf(p, s, 0.1994655728340149f);
+  p = fmaf(p, s, -0.33329859375953674f);
+  p = fmaf(p, s, 0.9999993443489075f);
+  float r = p * t;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.0f) r = 3.14159265358979324f - r;
+  return copysignf(r, y);
+}
+
+// Bilinear footprint at one level: integer top-left tap (>= -1) and the two weights. The coordinate is clamped as a float
+// first ([-1, size-1]); that selects the same taps and the same value as clamp-to-edge of the integer coordinates.
+struct Footprint {
+  int ix, iy;
   float a, b;
 };
-
-__device__ __forceinline__ Footprint footprint(const LevelView &l, float scaleX, float scaleY, float sx, float sy) {
+__device__ __forceinline__ Footprint footprint(const LevelGeom &g, float sx, float sy) {
   Footprint f;
-  const float u = fmaf(sx, scaleX, -0.5f), v = fmaf(sy, scaleY, -0.5f);
-  const float fu = floorf(u), fv = floorf(v);
-  f.a = u - fu;
-  f.b = v - fv;
-  const int ix = (int)fu, iy = (int)fv;
-  const int x0 = min(max(ix, 0), l.w - 1), x1 = min(max(ix + 1, 0), l.w - 1);
-  const int y0 = min(max(iy, 0), l.h - 1), y1 = min(max(iy + 1, 0), l.h - 1);
-  const int r0 = y0 * (int)(l.pitch >> 3), r1 = y1 * (int)(l.pitch >> 3); // both pyramid formats are 8 bytes per texel
-  f.o00 = r0 + x0;
-  f.o10 = r0 + x1;
-  f.o01 = r1 + x0;
-  f.o11 = r1 + x1;
+  const float u = fminf(fmaxf(fmaf(sx, g.scaleX, -0.5f), -1.0f), g.maxX), v = fminf(fmaxf(fmaf(sy, g.scaleY, -0.5f), -1.0f), g.maxY);
+  const float tu = __fadd_rd(u, kFloorMagic), tv = __fadd_rd(v, kFloorMagic);
+  f.a = u - (tu - kFloorMagic);
+  f.b = v - (tv - kFloorMagic);
+  f.ix = __float_as_int(tu) - kFloorMagicBits;
+  f.iy = __float_as_int(tv) - kFloorMagicBits;
   return f;
 }
 
-__device__ __forceinline__ float lerpf(float p, float q, float t) { return fmaf(q - p, t, p); }
-
-__device__ __forceinline__ float fetchDepth(const LevelView &l, const Footprint &f) {
-  const float2 *base = reinterpret_cast<const float2 *>(l.ptr);
-  const float t00 = __ldg(&base[f.o00].x), t10 = __ldg(&base[f.o10].x), t01 = __ldg(&base[f.o01].x), t11 = __ldg(&base[f.o11].x);
+template <bool kQuads>
+__device__ __forceinline__ float fetchDepth(const LevelGeom &g, const Footprint &f, const float4 *__restrict__ quads, const float2 *__restrict__ moments) {
+  float t00, t10, t01, t11;
+  if (kQuads) {
+    const float4 q = __ldg(quads + (unsigned)(g.quadOfs + (f.iy + 1) * g.quadPitch + (f.ix + 1)));
+    t00 = q.x, t10 = q.y, t01 = q.z, t11 = q.w;
+  } else {
+    const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, g.wm1), y0 = max(f.iy, 0), y1 = min(f.iy + 1, g.hm1);
+    const unsigned r0 = g.texOfs + y0 * g.texPitch, r1 = g.texOfs + y1 * g.texPitch;
+    t00 = __ldg(&moments[r0 + x0].x), t10 = __ldg(&moments[r0 + x1].x), t01 = __ldg(&moments[r1 + x0].x), t11 = __ldg(&moments[r1 + x1].x);
+  }
   return lerpf(lerpf(t00, t10, f.a), lerpf(t01, t11, f.a), f.b);
 }
 
-__device__ __forceinline__ float3 fetchLight(const LevelView &l, const Footprint &f) {
-  const uint2 *base = reinterpret_cast<const uint2 *>(l.ptr);
-  const uint2 r00 = __ldg(&base[f.o00]), r10 = __ldg(&base[f.o10]), r01 = __ldg(&base[f.o01]), r11 = __ldg(&base[f.o11]);
+__device__ __forceinline__ float3 fetchLight(const LevelGeom &g, const Footprint &f, const uint2 *__restrict__ light) {
+  const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, g.wm1), y0 = max(f.iy, 0), y1 = min(f.iy + 1, g.hm1);
+  const unsigned o0 = g.texOfs + y0 * g.texPitch, o1 = g.texOfs + y1 * g.texPitch;
+  const uint2 r00 = __ldg(&light[o0 + x0]), r10 = __ldg(&light[o0 + x1]), r01 = __ldg(&light[o1 + x0]), r11 = __ldg(&light[o1 + x1]);
   const float2 a00 = __half22float2(*reinterpret_cast<const __half2 *>(&r00.x)), a10 = __half22float2(*reinterpret_cast<const __half2 *>(&r10.x));
   const float2 a01 = __half22float2(*reinterpret_cast<const __half2 *>(&r01.x)), a11 = __half22float2(*reinterpret_cast<const __half2 *>(&r11.x));
   const float b00 = __low2float(*reinterpret_cast<const __half2 *>(&r00.y)), b10 = __low2float(*reinterpret_cast<const __half2 *>(&r10.y));
@@ -111,162 +156,161 @@ __device__ __forceinline__ float4 mulMat4Exact(const Mat4 &M, float x, float y, 
 }
 __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 
-__device__ __forceinline__ float dotf(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
-
-__global__ void __launch_bounds__(kThreads, 2) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb) {
-  __shared__ __align__(16) float4 stage[kTile * kTile]; // fp32 RGBA staging of the tile (16 KiB)
-
-  const int lane = threadIdx.x & 31, idx = threadIdx.x >> 5; // warp index == pattern index (x&3) + 4*(y&3)
-  const int tileX = blockIdx.x * kTile, tileY = a.rows.y0 + blockIdx.y * kTile;
+template <bool kQuads>
+__global__ void __launch_bounds__(kThreads, 4) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
+                                                                 const float4 *__restrict__ quads) {
+  const int t = threadIdx.x;
+  // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
+  const int tileX = blockIdx.x * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * kTile;
   const float vpx = a.viewport[0], vpy = a.viewport[1];
   const float invVpx = 1.0f / vpx, invVpy = 1.0f / vpy;
   const V3 cam = v3(a.cam[0], a.cam[1], a.cam[2]);
   const V3 Ra = v3(tb.ra[0], tb.ra[1], tb.ra[2]), Rb = v3(tb.rb[0], tb.rb[1], tb.rb[2]), Rc = v3(tb.rc[0], tb.rc[1], tb.rc[2]);
+  const float2 *__restrict__ moments = reinterpret_cast<const float2 *>(a.moments.lv[0].ptr);
+  const uint2 *__restrict__ light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
+  const int tx = 4 * (t & 15), ty = 4 * (t >> 4);
 
 #pragma unroll 1
-  for (int half = 0; half < 2; half++) {
-    const int lx = 4 * (lane & 7) + (idx & 3), ly = 4 * ((lane >> 3) + 4 * half) + (idx >> 2);
-    const int x = tileX + lx, y = tileY + ly;
-    float4 result = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-    if (x < a.indirect.w && y < a.rows.y1) {
-      const float px = (float)x + 0.5f, py = (float)y + 0.5f;
-      // --- centre reconstruction in the shader's order (:116-132, :182) -----------------------------------------------
-      const float cu = __fdiv_rn(px, vpx), cv = __fdiv_rn(py, vpy);
-      const float4 ns = Texel<F16>::load(a.normal, x, y);
-      const float zc = Texel<D32>::load(a.depthStencil, x, y).x;
-      const float4 vc = mulMat4Exact(a.invViewProj, __fadd_rn(__fmul_rn(cu, 2.0f), -1.0f), __fadd_rn(__fmul_rn(cv, 2.0f), -1.0f), zc, 1.0f);
-      const V3 C = v3(__fdiv_rn(vc.x, vc.w), __fdiv_rn(vc.y, vc.w), __fdiv_rn(vc.z, vc.w));
-      const V3 N = v3(ns.x, ns.y, ns.z);
-      const V3 E = v3(__fadd_rn(cam.x, -C.x), __fadd_rn(cam.y, -C.y), __fadd_rn(cam.z, -C.z)); // cam - C
-      const float invLenE = __fdiv_rn(1.0f, __fsqrt_rn(dot3Exact(E, E)));
-      const V3 eye = v3(__fmul_rn(E.x, invLenE), __fmul_rn(E.y, invLenE), __fmul_rn(E.z, invLenE));
-      const float eN = dot3Exact(eye, N);
-      // --- ray through the pixel: R0 ∝ far-plane point - cam ----------------------------------------------------------
-      const V3 R0 = v3(fmaf(Ra.x, px, fmaf(Rb.x, py, Rc.x)), fmaf(Ra.y, px, fmaf(Rb.y, py, Rc.y)), fmaf(Ra.z, px, fmaf(Rb.z, py, Rc.z)));
-      const float q0 = dotf(R0, R0);
-      const float n0 = sqrtf(q0);
-      const float xE = dotf(eye, E), xR0 = dotf(eye, R0);
-      float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
+  for (int idx = 0; idx < 16; idx++) { // one pattern class per pass (CTA-uniform)
+    const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
+    const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
+    if (!__any_sync(0xffffffffu, active)) continue;
+    const int cx = active ? x : 0, cy = active ? y : a.rows.y0; // inactive lanes shade a valid pixel and discard it
+    const float px = (float)cx + 0.5f, py = (float)cy + 0.5f;
+    // --- centre reconstruction in the shader's order (:116-132, :182) -------------------------------------------------
+    const float cu = __fdiv_rn(px, vpx), cv = __fdiv_rn(py, vpy);
+    const float4 ns = Texel<F16>::load(a.normal, cx, cy);
+    const float zc = Texel<D32>::load(a.depthStencil, cx, cy).x;
+    const float4 vc = mulMat4Exact(a.invViewProj, __fadd_rn(__fmul_rn(cu, 2.0f), -1.0f), __fadd_rn(__fmul_rn(cv, 2.0f), -1.0f), zc, 1.0f);
+    const V3 C = v3(__fdiv_rn(vc.x, vc.w), __fdiv_rn(vc.y, vc.w), __fdiv_rn(vc.z, vc.w));
+    const V3 N = v3(ns.x, ns.y, ns.z);
+    const V3 E = v3(__fadd_rn(cam.x, -C.x), __fadd_rn(cam.y, -C.y), __fadd_rn(cam.z, -C.z)); // cam - C
+    const float invLenE = __fdiv_rn(1.0f, __fsqrt_rn(dot3Exact(E, E)));
+    const V3 eye = v3(__fmul_rn(E.x, invLenE), __fmul_rn(E.y, invLenE), __fmul_rn(E.z, invLenE));
+    const float eN4 = 0.25f * dot3Exact(eye, N);
+    // --- ray through the pixel: R0 ∝ far-plane point - cam --------------------------------------------------------------
+    const V3 R0 = v3(fmaf(Ra.x, px, fmaf(Rb.x, py, Rc.x)), fmaf(Ra.y, px, fmaf(Rb.y, py, Rc.y)), fmaf(Ra.z, px, fmaf(Rb.z, py, Rc.z)));
+    const float q0 = dotf(R0, R0);
+    const float n0 = sqrtf(q0);
+    const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
+    float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
+    const StepRow *__restrict__ rows = &tb.row[idx * kMaxSteps];
 
 #pragma unroll 1
-      for (int d = 0; d < kGatherDirs; d++) {
-        const float dirx = tb.dirX[idx][d], diry = tb.dirY[idx][d];
-        const V3 Rd = v3(tb.rd[idx][d][0], tb.rd[idx][d][1], tb.rd[idx][d][2]);
-        // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
-        const float r0rd = dotf(R0, Rd), q2 = dotf(Rd, Rd);
-        const float q1 = 2.0f * r0rd;
-        const float n1 = sqrtf(q0 + q1 + q2);
-        const float g = (q1 + q2) * fastRcp(n0 + n1);
-        V3 tanU = v3(fmaf(Rd.x, n0, -R0.x * g), fmaf(Rd.y, n0, -R0.y * g), fmaf(Rd.z, n0, -R0.z * g));
-        const float tInv = tb.raySign * fastRsqrt(dotf(tanU, tanU));
-        const V3 tang = v3(tanU.x * tInv, tanU.y * tInv, tanU.z * tInv);
-        const float tN = dotf(tang, N);
-        // initial horizon from the surface normal (:193-198)
-        const V3 bn = cross3(eye, tang); // -cross(tangent, eye)
-        const V3 q = cross3(bn, N);
-        float mx = dotf(q, eye), my = dotf(q, tang);
-        float maxH = atan2f(my, mx);
-        float invM = fastRcp(fmaxf(fmaf(mx, mx, my * my), 1e-37f));
-        float c2m = (mx * mx - my * my) * invM, s2m = 2.0f * mx * my * invM;
-        // BoxRayCast + iteration count (:83-99, :202-212), exact like the strict kernel
-        const float ivx = __fdiv_rn(1.0f, dirx), ivy = __fdiv_rn(1.0f, diry);
-        const float t1 = __fmul_rn(0.0f - px, ivx), t2 = __fmul_rn(vpx - px, ivx), t3 = __fmul_rn(0.0f - py, ivy), t4 = __fmul_rn(vpy - py, ivy);
-        const float path = fabsf(glmMin(glmMax(t1, t2), glmMax(t3, t4)));
-        int iterations = 0;
-        for (int n = 0; n < tb.maxSteps; n++) iterations += (path >= tb.iterThreshold[n]) ? 1 : 0;
-        // ambient term 0.01 * HC(0, maxH) (:209): cos(0) = 1, sin(0) = 0
-        const float hc0 = 0.25f * eN * (1.0f - c2m) + 0.25f * tN * (2.0f * maxH - s2m);
-        float Lx = 0.01f * hc0, Ly = Lx, Lz = Lx;
-        // per-direction affine coefficients of the horizon vector
-        const float yE = dotf(tang, E), yR0 = dotf(tang, R0), xRd = dotf(eye, Rd), yRd = dotf(tang, Rd);
+    for (int d = 0; d < kGatherDirs; d++) {
+      const DirEntry de = tb.dir[idx][d];
+      const V3 Rd = v3(de.rdX, de.rdY, de.rdZ);
+      // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
+      const float q2 = de.q2, q1 = 2.0f * dotf(R0, Rd);
+      const float n1 = sqrtf(q0 + q1 + q2);
+      const float g = (q1 + q2) * fastRcp(n0 + n1);
+      const V3 tanU = v3(fmaf(Rd.x, n0, -R0.x * g), fmaf(Rd.y, n0, -R0.y * g), fmaf(Rd.z, n0, -R0.z * g));
+      const float tInv = tb.raySign * fastRsqrt(dotf(tanU, tanU));
+      const V3 tang = v3(tanU.x * tInv, tanU.y * tInv, tanU.z * tInv);
+      const float tN4 = 0.25f * dotf(tang, N);
+      // initial horizon from the surface normal (:193-198)
+      const V3 bn = cross3(eye, tang); // -cross(tangent, eye)
+      const V3 q = cross3(bn, N);
+      float mx = dotf(q, eye), my = dotf(q, tang);
+      float maxH = atan2Poly(my, mx);
+      const float invM = fastRcp(fmaxf(fmaf(mx, mx, my * my), 1e-37f));
+      float c2m = (mx * mx - my * my) * invM, s2m = 2.0f * mx * my * invM;
+      // BoxRayCast + iteration count (:83-99, :202-212), exact like the strict kernel
+      const float t1 = __fmul_rn(0.0f - px, de.invDirX), t2 = __fmul_rn(vpx - px, de.invDirX);
+      const float t3 = __fmul_rn(0.0f - py, de.invDirY), t4 = __fmul_rn(vpy - py, de.invDirY);
+      const float path = fabsf(glmMin(glmMax(t1, t2), glmMax(t3, t4)));
+      int iterations = 0;
+#pragma unroll
+      for (int n = 0; n < kMaxSteps; n++) iterations += (path >= tb.iterThreshold[n]) ? 1 : 0; // thresholds beyond maxSteps are +inf
+      if (!active) iterations = 0;
+      // ambient term 0.01 * HC(0, maxH) (:209): cos(0) = 1, sin(0) = 0.  L = sum(Ls*c) - 0.01*sum(c) + 0.01*hc0
+      float Lx = 0.0f, Ly = 0.0f, Lz = 0.0f;
+      float cSum = -(eN4 * (1.0f - c2m) + tN4 * (2.0f * maxH - s2m));
+      // per-direction affine coefficients of the horizon vector
+      const float yE = dotf(tang, E), yR0 = tb.raySign * dotf(tang, R0);
+      const float xRd = tb.raySign * dotf(eye, Rd), yRd = tb.raySign * dotf(tang, Rd);
 
+      const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
 #pragma unroll 1
-        for (int k = 0; k < iterations; k++) {
-          const float off = tb.pixelOffset[idx][k];
-          const int d0 = tb.lod0[idx][k], d1 = tb.lod1[idx][k];
-          const float frac = tb.lodFrac[idx][k];
-          const float sx = fmaf(dirx, off, px), sy = fmaf(diry, off, py);
-          const Footprint f0 = footprint(a.moments.lv[d0], tb.levelScaleX[d0], tb.levelScaleY[d0], sx, sy);
-          float z = fetchDepth(a.moments.lv[d0], f0);
-          Footprint f1 = f0;
-          if (frac > 0.0f) { // warp-uniform
-            f1 = footprint(a.moments.lv[d1], tb.levelScaleX[d1], tb.levelScaleY[d1], sx, sy);
-            z = fmaf(frac, fetchDepth(a.moments.lv[d1], f1) - z, z); // (1-frac)*lo + frac*hi
-          }
-          const float rs = fastRsqrt(fmaf(off, fmaf(off, q2, q1), q0)); // 1 / |R(s)|
-          const float zs = tb.raySign * z * rs;
-          const float hx = fmaf(zs, fmaf(off, xRd, xR0), xE); // dot(eye, P - C)
-          const float hy = fmaf(zs, fmaf(off, yRd, yR0), yE); // dot(tangent, P - C)
-          // h < maxH for angles in (-pi, pi]: different half planes decide directly, otherwise the cross product does
-          const bool lower = hy < 0.0f, lowerM = my < 0.0f;
-          const bool maybe = (lower != lowerM) ? lower : (hx * my - hy * mx > 0.0f);
-          if (maybe) {
-            const float h = atan2f(hy, hx);
-            if (h < maxH) { // :254
-              const float su = sx * invVpx, sv = sy * invVpy;
-              float side = saturatef((1.0f - su) * 10.0f);
-              side *= saturatef(su * 10.0f);
-              side *= saturatef((1.0f - sv) * 10.0f);
-              side *= saturatef(sv * 10.0f);
-              float3 ls = fetchLight(a.light.lv[d0], f0);
-              if (frac > 0.0f) {
-                const float3 hi = fetchLight(a.light.lv[d1], f1);
-                ls.x = fmaf(frac, hi.x - ls.x, ls.x);
-                ls.y = fmaf(frac, hi.y - ls.y, ls.y);
-                ls.z = fmaf(frac, hi.z - ls.z, ls.z);
-              }
-              const float inv = fastRcp(fmaxf(fmaf(hx, hx, hy * hy), 1e-37f));
-              const float c2 = (hx * hx - hy * hy) * inv, s2 = 2.0f * hx * hy * inv;
-              const float hc = 0.25f * eN * (c2 - c2m) + 0.25f * tN * (((2.0f * maxH - 2.0f * h) - s2m) + s2);
-              const float c = hc * side;
-              Lx = fmaf(ls.x - 0.01f, c, Lx);
-              Ly = fmaf(ls.y - 0.01f, c, Ly);
-              Lz = fmaf(ls.z - 0.01f, c, Lz);
-              maxH = h;
-              c2m = c2;
-              s2m = s2;
-              mx = hx;
-              my = hy;
-            }
-          }
+      for (int k = 0; k < warpIters; k++) { // :214
+        const StepRow &st = rows[k];
+        const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
+        const Footprint f0 = footprint(st.g0, sx, sy);
+        Footprint f1 = f0;
+        float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
+        if (st.frac > 0.0f) { // uniform branch
+          f1 = footprint(st.g1, sx, sy);
+          z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
         }
-        sumX = fmaf(0.5f, Lx, sumX);
-        sumY = fmaf(0.5f, Ly, sumY);
-        sumZ = fmaf(0.5f, Lz, sumZ);
+        const float zs = z * fastRsqrt(fmaf(st.off, fmaf(st.off, q2, q1), q0)); // z / |R(s)|
+        const float hx = fmaf(zs, fmaf(st.off, xRd, xR0), xE); // dot(eye, P - C)      :241-252
+        const float hy = fmaf(zs, fmaf(st.off, yRd, yR0), yE); // dot(tangent, P - C)
+        // h < maxH for angles in (-pi, pi]: different half planes decide directly, otherwise the cross product does
+        const bool lower = hy < 0.0f, lowerM = my < 0.0f;
+        const bool hit = (lower != lowerM) ? lower : (hx * my - hy * mx > 0.0f);
+        if (hit && k < iterations) { // :254
+          const float h = atan2Poly(hy, hx);
+          const float inv = fastRcp(fmaxf(fmaf(hx, hx, hy * hy), 1e-37f));
+          const float c2 = (hx * hx - hy * hy) * inv, s2 = 2.0f * hx * hy * inv;
+          const float hc = eN4 * (c2 - c2m) + tN4 * (((2.0f * maxH - 2.0f * h) - s2m) + s2); // :44-49
+          const float su = sx * invVpx, sv = sy * invVpy;
+          // product of the four saturates of :220-228 (at most one per axis is below 1)
+          const float side = saturatef(fminf(su, 1.0f - su) * 10.0f) * saturatef(fminf(sv, 1.0f - sv) * 10.0f);
+          float3 ls = fetchLight(st.g0, f0, light); // :256
+          if (st.frac > 0.0f) {
+            const float3 hi = fetchLight(st.g1, f1, light);
+            ls.x = fmaf(st.frac, hi.x - ls.x, ls.x);
+            ls.y = fmaf(st.frac, hi.y - ls.y, ls.y);
+            ls.z = fmaf(st.frac, hi.z - ls.z, ls.z);
+          }
+          const float c = hc * side; // :258
+          Lx = fmaf(ls.x, c, Lx);    // :261
+          Ly = fmaf(ls.y, c, Ly);
+          Lz = fmaf(ls.z, c, Lz);
+          cSum += c;                 // :262
+          maxH = h;                  // :263
+          c2m = c2;
+          s2m = s2;
+          mx = hx;
+          my = hy;
+        }
       }
-      result = make_float4(sumX, sumY, sumZ, 1.0f);
+      const float amb = -0.01f * cSum;
+      sumX = fmaf(0.5f, Lx + amb, sumX); // :268
+      sumY = fmaf(0.5f, Ly + amb, sumY);
+      sumZ = fmaf(0.5f, Lz + amb, sumZ);
     }
-    stage[ly * kTile + lx] = result;
-  }
-  __syncthreads();
-
-  // coalesced write-out of the tile
-  if (a.outFormat == F16) {
-    // 32 rows x 32 px x 8 B: 16 threads per row, 16 bytes (2 px) each
-    const int row = threadIdx.x >> 4, col = (threadIdx.x & 15) * 2;
-    const int x = tileX + col, y = tileY + row;
-    if (y < a.rows.y1 && x < a.indirect.w) {
-      const uint2 p0 = Texel<F16>::pack(stage[row * kTile + col]);
-      unsigned char *dst = a.indirect.ptr + (size_t)y * a.indirect.pitch + (size_t)x * 8;
-      if (x + 1 < a.indirect.w) {
-        const uint2 p1 = Texel<F16>::pack(stage[row * kTile + col + 1]);
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(p0.x, p0.y, p1.x, p1.y);
-      } else {
-        *reinterpret_cast<uint2 *>(dst) = p0;
-      }
-    }
-  } else {
-    for (int i = threadIdx.x; i < kTile * kTile; i += kThreads) {
-      const int row = i >> 5, col = i & 31;
-      const int x = tileX + col, y = tileY + row;
-      if (y < a.rows.y1 && x < a.indirect.w) reinterpret_cast<float4 *>(a.indirect.ptr + (size_t)y * a.indirect.pitch)[x] = stage[i];
-    }
+    if (active) storeColor(a.outFormat, a.indirect, x, y, make_float4(sumX, sumY, sumZ, 1.0f)); // :270
   }
 }
 
+// Quad-packed depth pyramid: entry (qx, qy) of level l, qx in [0, w], qy in [0, h], holds the .r taps
+// {(x0,y0), (x1,y0), (x0,y1), (x1,y1)} with x0 = clamp(qx-1), x1 = clamp(qx), y0 = clamp(qy-1), y1 = clamp(qy).
+struct PackArgs {
+  PyramidView moments;
+  int quadOfs[kMaxGatherLevels], quadPitch[kMaxGatherLevels], quadRows[kMaxGatherLevels];
+  int rowBegin[kMaxGatherLevels], rowEnd[kMaxGatherLevels]; // quad rows to (re)build per level
+  int blockBegin[kMaxGatherLevels + 1];                      // first CTA of each level (32x8 quads per CTA)
+  int levels;
+};
+
+__global__ void __launch_bounds__(256) packDepthQuadsKernel(const __grid_constant__ PackArgs p, float4 *__restrict__ quads) {
+  int l = 0;
+  while (l + 1 < p.levels && (int)blockIdx.x >= p.blockBegin[l + 1]) l++;
+  const LevelView lv = p.moments.lv[l];
+  const int bx = (p.quadPitch[l] + 31) / 32;
+  const int b = blockIdx.x - p.blockBegin[l];
+  const int qx = (b % bx) * 32 + (threadIdx.x & 31), qy = p.rowBegin[l] + (b / bx) * 8 + (threadIdx.x >> 5);
+  if (qx >= p.quadPitch[l] || qy >= p.rowEnd[l]) return;
+  const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
+  const float *r0 = reinterpret_cast<const float *>(lv.ptr + (size_t)y0 * lv.pitch), *r1 = reinterpret_cast<const float *>(lv.ptr + (size_t)y1 * lv.pitch);
+  quads[(size_t)p.quadOfs[l] + (size_t)qy * p.quadPitch[l] + qx] = make_float4(__ldg(r0 + 2 * x0), __ldg(r0 + 2 * x1), __ldg(r1 + 2 * x0), __ldg(r1 + 2 * x1));
+}
+
 // Host: derive the fast tables. Returns false if the projection is not of the form the affine ray model assumes
-// (homogeneous w of the far-plane point must not change sign over the screen) -> caller uses the strict kernel.
+// (homogeneous w of the far-plane point must not change sign over the screen) or the tables do not fit -> strict kernel.
 bool buildFastTables(const GatherArgs &a, const GatherTables &t, FastTables *f) {
+  if (t.maxSteps > kMaxSteps) return false;
   const double vpx = a.viewport[0], vpy = a.viewport[1];
   const float *m = a.invViewProj.m;
   double A4[4], B4[4], D4[4];
@@ -303,44 +347,118 @@ bool buildFastTables(const GatherArgs &a, const GatherTables &t, FastTables *f) 
   }
   f->raySign = float(sign);
   f->maxSteps = t.maxSteps;
-  for (int n = 0; n < kGatherMaxSteps; n++) f->iterThreshold[n] = t.iterThreshold[n];
+  for (int n = 0; n < kMaxSteps; n++) f->iterThreshold[n] = t.iterThreshold[n];
   for (int idx = 0; idx < 16; idx++) {
     for (int d = 0; d < kGatherDirs; d++) {
-      f->dirX[idx][d] = t.dirX[idx][d];
-      f->dirY[idx][d] = t.dirY[idx][d];
-      for (int i = 0; i < 3; i++) f->rd[idx][d][i] = float((ra[i] * double(t.dirX[idx][d]) + rb[i] * double(t.dirY[idx][d])) / len);
+      DirEntry &de = f->dir[idx][d];
+      de.dirX = t.dirX[idx][d];
+      de.dirY = t.dirY[idx][d];
+      de.invDirX = 1.0f / de.dirX; // :87 (IEEE divide, like the shader's vec2(1) / rayDir)
+      de.invDirY = 1.0f / de.dirY;
+      double rd[3];
+      for (int i = 0; i < 3; i++) rd[i] = (ra[i] * double(de.dirX) + rb[i] * double(de.dirY)) / len;
+      de.rdX = float(rd[0]);
+      de.rdY = float(rd[1]);
+      de.rdZ = float(rd[2]);
+      de.q2 = float(double(de.rdX) * de.rdX + double(de.rdY) * de.rdY + double(de.rdZ) * de.rdZ);
     }
-    for (int k = 0; k < kGatherMaxSteps; k++) {
+    for (int k = 0; k < kMaxSteps; k++) {
       const float lambda = t.lod[idx][k];
       const float fl = std::floor(lambda);
       const int d0 = int(fl);
-      f->pixelOffset[idx][k] = t.pixelOffset[idx][k];
-      f->lodFrac[idx][k] = lambda - fl;
-      f->lod0[idx][k] = (signed char)d0;
-      f->lod1[idx][k] = (signed char)(d0 + 1 < a.moments.count ? d0 + 1 : a.moments.count - 1);
+      StepRow &st = f->row[idx * kMaxSteps + k];
+      st.off = t.pixelOffset[idx][k];
+      st.frac = lambda - fl;
+      st.l0 = d0;
+      st.l1 = d0 + 1 < a.moments.count ? d0 + 1 : a.moments.count - 1;
     }
   }
-  for (int l = 0; l < kMaxGatherLevels; l++) {
-    const int w = l < a.moments.count ? a.moments.lv[l].w : 1, h = l < a.moments.count ? a.moments.lv[l].h : 1;
-    f->levelScaleX[l] = float(double(w) / vpx);
-    f->levelScaleY[l] = float(double(h) / vpy);
+  return true;
+}
+
+// Level geometry of the march rows and of the packer. Returns false if the two pyramids do not share one layout.
+bool buildLevelGeometry(const GatherArgs &a, FastTables *f, PackArgs *p) {
+  const double vpx = a.viewport[0], vpy = a.viewport[1];
+  LevelGeom geom[kMaxGatherLevels];
+  long long quadOfs = 0;
+  for (int l = 0; l < a.moments.count; l++) {
+    LevelGeom &g = geom[l];
+    const LevelView &mv = a.moments.lv[l], &lv = a.light.lv[l];
+    const long long mOfs = mv.ptr - a.moments.lv[0].ptr, lOfs = lv.ptr - a.light.lv[0].ptr;
+    if (mv.w != lv.w || mv.h != lv.h || mv.pitch != lv.pitch || mOfs != lOfs || (mv.pitch % 8) != 0 || (mOfs % 8) != 0 ||
+        (mOfs + (long long)mv.pitch * mv.h) / 8 > 0x7fffffffLL)
+      return false;
+    g.scaleX = float(double(mv.w) / vpx);
+    g.scaleY = float(double(mv.h) / vpy);
+    g.maxX = float(mv.w - 1);
+    g.maxY = float(mv.h - 1);
+    g.texOfs = int(mOfs / 8);
+    g.texPitch = int(mv.pitch / 8);
+    g.wm1 = mv.w - 1;
+    g.hm1 = mv.h - 1;
+    g.quadOfs = int(quadOfs);
+    g.quadPitch = mv.w + 1;
+    g.pad0 = g.pad1 = 0;
+    if (p) {
+      p->quadOfs[l] = g.quadOfs;
+      p->quadPitch[l] = g.quadPitch;
+      p->quadRows[l] = mv.h + 1;
+    }
+    quadOfs += (long long)(mv.w + 1) * (mv.h + 1);
+    if (quadOfs > 0x7fffffffLL) return false;
   }
+  if (f)
+    for (int r = 0; r < 16 * kMaxSteps; r++) {
+      f->row[r].g0 = geom[f->row[r].l0];
+      f->row[r].g1 = geom[f->row[r].l1];
+    }
   return true;
 }
 
 } // namespace
 
-cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, cudaStream_t s) {
+uint64_t gatherScratchBytes(uint32_t width, uint32_t height, uint32_t mips) {
+  uint64_t quads = 0;
+  for (uint32_t l = 0; l < mips && l < (uint32_t)kMaxGatherLevels; l++) {
+    const uint64_t w = (width >> l) ? (width >> l) : 1, h = (height >> l) ? (height >> l) : 1;
+    quads += (w + 1) * (h + 1);
+  }
+  return quads * sizeof(float4);
+}
+
+cudaError_t launchGatherPack(const GatherArgs &a, void *scratch, cudaStream_t s) {
+  PackArgs p;
+  if (!buildLevelGeometry(a, nullptr, &p)) return cudaErrorInvalidValue;
+  p.moments = a.moments;
+  p.levels = a.moments.count;
+  int blocks = 0;
+  for (int l = 0; l < p.levels; l++) {
+    // strip: the march reaches ~13 level-l texels beyond the strip; the coarse levels are rebuilt whole
+    const int reach = 16;
+    int r0 = (a.rows.y0 >> l) - reach, r1 = ((a.rows.y1 + (1 << l) - 1) >> l) + reach + 1;
+    const bool whole = l >= 6 || l == p.levels - 1; // the top level serves every clamped LOD
+    if (whole || r0 < 0) r0 = 0;
+    if (whole || r1 > p.quadRows[l]) r1 = p.quadRows[l];
+    p.rowBegin[l] = r0;
+    p.rowEnd[l] = r1;
+    p.blockBegin[l] = blocks;
+    blocks += ((p.quadPitch[l] + 31) / 32) * ((r1 - r0 + 7) / 8);
+  }
+  p.blockBegin[p.levels] = blocks;
+  if (blocks == 0) return cudaSuccess;
+  packDepthQuadsKernel<<<blocks, 256, 0, s>>>(p, static_cast<float4 *>(scratch));
+  return cudaGetLastError();
+}
+
+cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const void *scratch, cudaStream_t s) {
   if (a.rows.y1 <= a.rows.y0) return cudaSuccess;
   FastTables f;
-  // the tile / pattern mapping needs the strip to start on a pattern row; both pyramids must share their geometry
-  bool ok = (a.rows.y0 % 4) == 0 && buildFastTables(a, t, &f);
-  for (int l = 0; ok && l < a.moments.count; l++)
-    ok = a.moments.lv[l].w == a.light.lv[l].w && a.moments.lv[l].h == a.light.lv[l].h && a.moments.lv[l].pitch == a.light.lv[l].pitch &&
-         (a.moments.lv[l].pitch % 8) == 0;
-  if (!ok) return launchGatherStrict(a, t, s);
-  const dim3 grid((a.indirect.w + kTile - 1) / kTile, (a.rows.y1 - a.rows.y0 + kTile - 1) / kTile);
-  gatherFastKernel<<<grid, kThreads, 0, s>>>(a, f);
+  if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, &f, nullptr)) return launchGatherStrict(a, t, s);
+  const dim3 grid((a.indirect.w + kTile - 1) / kTile, (a.rows.y1 - (a.rows.y0 & ~3) + kTile - 1) / kTile);
+  if (scratch)
+    gatherFastKernel<true><<<grid, kThreads, 0, s>>>(a, f, static_cast<const float4 *>(scratch));
+  else
+    gatherFastKernel<false><<<grid, kThreads, 0, s>>>(a, f, nullptr);
   return cudaGetLastError();
 }
 

@@ -384,39 +384,90 @@ int lgcu_mip_blur_chain(const lgcu_image *chain, const lgcu_image *blurred, int3
 }
 
 // ------------------------------------------------------------------------------------------------------- K5
+static bool fillGatherArgs(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
+                           const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, const lgcu_rows *rows, GatherArgs *a,
+                           int *st) {
+  if (!params) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather: null params");
+    return false;
+  }
+  if (!expectFormat(blurredDirectLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, "blurredDirectLight", st) ||
+      !expectFormat(blurredDepthMoments, LGCU_FORMAT_R32G32_SFLOAT, "blurredDepthMoments", st) ||
+      !expectFormat(normal, LGCU_FORMAT_R16G16B16A16_SFLOAT, "normal", st) || !expectFormat(depthStencil, LGCU_FORMAT_D32_SFLOAT, "depthStencil", st))
+    return false;
+  if (!indirectLight || (indirectLight->format != LGCU_FORMAT_R16G16B16A16_SFLOAT && indirectLight->format != LGCU_FORMAT_R32G32B32A32_SFLOAT)) {
+    *st = fail(LGCU_ERR_UNSUPPORTED_FORMAT, "indirectLight: format %u", indirectLight ? indirectLight->format : 0u);
+    return false;
+  }
+  a->outFormat = indirectLight->format;
+  if (!resolvePyramid(blurredDirectLight, "blurredDirectLight", &a->light, st) || !resolvePyramid(blurredDepthMoments, "blurredDepthMoments", &a->moments, st))
+    return false;
+  if (a->light.count != a->moments.count) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather: pyramids have %d and %d levels", a->light.count, a->moments.count);
+    return false;
+  }
+  if (!resolveLevel(normal, 0, "normal", &a->normal, st) || !resolveLevel(depthStencil, 0, "depthStencil", &a->depthStencil, st) ||
+      !resolveLevel(indirectLight, 0, "indirectLight", &a->indirect, st))
+    return false;
+  if (!sameSize(a->indirect, a->normal, "indirectLight", "normal", st) || !sameSize(a->indirect, a->depthStencil, "indirectLight", "depthStencil", st) ||
+      !sameSize(a->light.lv[0], a->moments.lv[0], "blurredDirectLight", "blurredDepthMoments", st))
+    return false;
+  const lgcu_mat4 viewProj = lgcu_mat4_mul(&params->projMatrix, &params->viewMatrix); // :122
+  a->invViewProj = toMat4(lgcu_mat4_inverse(&viewProj));                             // :123
+  const lgcu_mat4 invView = lgcu_mat4_inverse(&params->viewMatrix);                  // :124
+  originOf(invView, a->cam);                                                         // :127
+  a->viewport[0] = params->viewportExtent[0];
+  a->viewport[1] = params->viewportExtent[1];
+  a->rows = rowRange(rows, 0, a->indirect.h);
+  return true;
+}
+
+static bool checkScratch(const GatherArgs &a, const lgcu_image *moments, const void *scratch, uint64_t scratchBytes, int *st) {
+  const uint64_t need = gatherScratchBytes(moments->width >> moments->baseMip, moments->height >> moments->baseMip, (uint32_t)a.moments.count);
+  if (!scratch || (reinterpret_cast<uintptr_t>(scratch) % 16) != 0 || scratchBytes < need) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather: scratch %p / %llu bytes, need %llu bytes, 16-byte aligned", scratch, (unsigned long long)scratchBytes,
+               (unsigned long long)need);
+    return false;
+  }
+  return true;
+}
+
 int lgcu_gi_gather(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
                    const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, uint32_t flags, const lgcu_rows *rows,
                    void *stream) {
   int st = LGCU_OK;
-  if (!params) return fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather: null params");
-  if (!expectFormat(blurredDirectLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, "blurredDirectLight", &st) ||
-      !expectFormat(blurredDepthMoments, LGCU_FORMAT_R32G32_SFLOAT, "blurredDepthMoments", &st) ||
-      !expectFormat(normal, LGCU_FORMAT_R16G16B16A16_SFLOAT, "normal", &st) || !expectFormat(depthStencil, LGCU_FORMAT_D32_SFLOAT, "depthStencil", &st))
-    return st;
-  if (!indirectLight || (indirectLight->format != LGCU_FORMAT_R16G16B16A16_SFLOAT && indirectLight->format != LGCU_FORMAT_R32G32B32A32_SFLOAT))
-    return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "indirectLight: format %u", indirectLight ? indirectLight->format : 0u);
   GatherArgs a;
-  a.outFormat = indirectLight->format;
-  if (!resolvePyramid(blurredDirectLight, "blurredDirectLight", &a.light, &st) || !resolvePyramid(blurredDepthMoments, "blurredDepthMoments", &a.moments, &st))
-    return st;
-  if (a.light.count != a.moments.count) return fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather: pyramids have %d and %d levels", a.light.count, a.moments.count);
-  if (!resolveLevel(normal, 0, "normal", &a.normal, &st) || !resolveLevel(depthStencil, 0, "depthStencil", &a.depthStencil, &st) ||
-      !resolveLevel(indirectLight, 0, "indirectLight", &a.indirect, &st))
-    return st;
-  if (!sameSize(a.indirect, a.normal, "indirectLight", "normal", &st) || !sameSize(a.indirect, a.depthStencil, "indirectLight", "depthStencil", &st) ||
-      !sameSize(a.light.lv[0], a.moments.lv[0], "blurredDirectLight", "blurredDepthMoments", &st))
-    return st;
-  const lgcu_mat4 viewProj = lgcu_mat4_mul(&params->projMatrix, &params->viewMatrix); // :122
-  a.invViewProj = toMat4(lgcu_mat4_inverse(&viewProj));                             // :123
-  const lgcu_mat4 invView = lgcu_mat4_inverse(&params->viewMatrix);                 // :124
-  originOf(invView, a.cam);                                                         // :127
-  a.viewport[0] = params->viewportExtent[0];
-  a.viewport[1] = params->viewportExtent[1];
-  a.rows = rowRange(rows, 0, a.indirect.h);
+  if (!fillGatherArgs(params, blurredDirectLight, blurredDepthMoments, normal, depthStencil, indirectLight, rows, &a, &st)) return st;
   GatherTables tables;
   if (!buildGatherTables(a.viewport[0], a.viewport[1], a.light.count, &tables, &st)) return st;
   if (flags & LGCU_GI_STRICT) return cudaStatus(launchGatherStrict(a, tables, static_cast<cudaStream_t>(stream)), "gi_gather(strict)");
-  return cudaStatus(launchGatherFast(a, tables, static_cast<cudaStream_t>(stream)), "gi_gather");
+  return cudaStatus(launchGatherFast(a, tables, nullptr, static_cast<cudaStream_t>(stream)), "gi_gather");
+}
+
+uint64_t lgcu_gather_scratch_bytes(uint32_t width, uint32_t height, uint32_t mips) { return gatherScratchBytes(width, height, mips); }
+
+int lgcu_gi_gather_pack(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
+                        const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, void *scratch, uint64_t scratchBytes,
+                        const lgcu_rows *rows, void *stream) {
+  int st = LGCU_OK;
+  GatherArgs a;
+  if (!fillGatherArgs(params, blurredDirectLight, blurredDepthMoments, normal, depthStencil, indirectLight, rows, &a, &st)) return st;
+  if (!checkScratch(a, blurredDepthMoments, scratch, scratchBytes, &st)) return st;
+  const cudaError_t e = launchGatherPack(a, scratch, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidValue) return fail(LGCU_ERR_INVALID_ARGUMENT, "gi_gather_pack: the two pyramids must share one memory layout");
+  return cudaStatus(e, "gi_gather_pack");
+}
+
+int lgcu_gi_gather_packed(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
+                          const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, const void *scratch,
+                          uint64_t scratchBytes, const lgcu_rows *rows, void *stream) {
+  int st = LGCU_OK;
+  GatherArgs a;
+  if (!fillGatherArgs(params, blurredDirectLight, blurredDepthMoments, normal, depthStencil, indirectLight, rows, &a, &st)) return st;
+  if (!checkScratch(a, blurredDepthMoments, scratch, scratchBytes, &st)) return st;
+  GatherTables tables;
+  if (!buildGatherTables(a.viewport[0], a.viewport[1], a.light.count, &tables, &st)) return st;
+  return cudaStatus(launchGatherFast(a, tables, scratch, static_cast<cudaStream_t>(stream)), "gi_gather_packed");
 }
 
 // ------------------------------------------------------------------------------------------------------- K6 / K7

@@ -110,7 +110,10 @@ cudaError_t launchMipLevel(const MipLevelArgs &a, cudaStream_t s);
 cudaError_t launchBlurLevel(const BlurLevelArgs &a, cudaStream_t s);
 cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s);
 cudaError_t launchGatherStrict(const GatherArgs &a, const GatherTables &t, cudaStream_t s);
-cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, cudaStream_t s);
+// scratch == nullptr: individual depth taps; else the quad-packed depth pyramid built by launchGatherPack for the same views
+cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const void *scratch, cudaStream_t s);
+cudaError_t launchGatherPack(const GatherArgs &a, void *scratch, cudaStream_t s);
+uint64_t gatherScratchBytes(uint32_t width, uint32_t height, uint32_t mips);
 cudaError_t launchDenoise(const DenoiseArgs &a, cudaStream_t s);
 cudaError_t launchFinalGather(const FinalGatherArgs &a, cudaStream_t s);
 cudaError_t launchDenoiseFinalGather(const DenoiseFinalArgs &a, cudaStream_t s);

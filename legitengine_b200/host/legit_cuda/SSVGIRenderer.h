@@ -227,29 +227,67 @@ public:
 
     // calculating indirect lighting (:223-263)
     const uint32_t giFlags = options.giFlags;
-    graph->AddPass(RenderGraph::RenderPassDesc()
-                       .SetColorAttachments({res->indirectLight.imageViewProxy->Id()})
-                       .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
-                                        res->depthStencil.imageViewProxy->Id()})
-                       .SetRenderAreaExtent(viewportExtent)
-                       .SetProfilerInfo(Colors::sunFlower, "IndirectLightPass")
-                       .SetRecordFunc([this, passData, giFlags, rowsOf](RenderGraph::RenderPassContext passContext) {
-                         passData.memoryPool->BeginSet();
-                         auto shaderDataBuffer = passData.memoryPool->GetUniformBufferData<lgcu_indirect_lighting_data>("IndirectLightingData");
-                         shaderDataBuffer->viewMatrix = passData.viewMatrix;
-                         shaderDataBuffer->projMatrix = passData.projMatrix;
-                         shaderDataBuffer->viewportExtent[0] = float(this->viewportExtent.width);
-                         shaderDataBuffer->viewportExtent[1] = float(this->viewportExtent.height);
-                         shaderDataBuffer->viewportExtent[2] = shaderDataBuffer->viewportExtent[3] = 0.0f;
-                         passData.memoryPool->EndSet();
-                         ViewportResources *r = this->viewportResources.get();
-                         LgcuCheck(lgcu_gi_gather(shaderDataBuffer, passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(), // "blurredDirectLightSampler"
-                                                  passContext.GetImageView(r->blurredDepthMoments.imageViewProxy->Id())->GetDesc(),                // "blurredDepthMomentsSampler"
-                                                  passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),                             // "normalSampler"
-                                                  passContext.GetImageView(r->depthStencil.imageViewProxy->Id())->GetDesc(),                       // "depthStencilSampler"
-                                                  passContext.GetColorAttachment(0)->GetDesc(), giFlags, rowsOf(passData), passContext.GetStream()),
-                                   "IndirectLightPass");
-                       }));
+    const bool packedGather = options.mode == FrameOptions::Mode::Fused && !(giFlags & LGCU_GI_STRICT);
+    auto fillIndirectData = [this](const PassData &pd) {
+      pd.memoryPool->BeginSet();
+      auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_indirect_lighting_data>("IndirectLightingData");
+      shaderDataBuffer->viewMatrix = pd.viewMatrix;
+      shaderDataBuffer->projMatrix = pd.projMatrix;
+      shaderDataBuffer->viewportExtent[0] = float(this->viewportExtent.width);
+      shaderDataBuffer->viewportExtent[1] = float(this->viewportExtent.height);
+      shaderDataBuffer->viewportExtent[2] = shaderDataBuffer->viewportExtent[3] = 0.0f;
+      pd.memoryPool->EndSet();
+      return shaderDataBuffer;
+    };
+    if (packedGather) {
+      // builds the gather's private acceleration structure (quad-packed depth pyramid) in a transient buffer
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                                          res->depthStencil.imageViewProxy->Id(), res->indirectLight.imageViewProxy->Id()})
+                         .SetStorageBuffers({res->gatherScratch->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::carrot, "GatherPackPass")
+                         .SetRecordFunc([this, passData, fillIndirectData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillIndirectData(passData);
+                           ViewportResources *r = this->viewportResources.get();
+                           Buffer *scratch = passContext.GetBuffer(r->gatherScratch->Id());
+                           LgcuCheck(lgcu_gi_gather_pack(shaderDataBuffer, passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(),
+                                                         passContext.GetImageView(r->blurredDepthMoments.imageViewProxy->Id())->GetDesc(),
+                                                         passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc(),
+                                                         passContext.GetImageView(r->depthStencil.imageViewProxy->Id())->GetDesc(),
+                                                         passContext.GetImageView(r->indirectLight.imageViewProxy->Id())->GetDesc(), scratch->GetHandle(),
+                                                         scratch->GetSize(), rowsOf(passData), passContext.GetStream()),
+                                     "GatherPackPass");
+                         }));
+    }
+    {
+      RenderGraph::RenderPassDesc desc;
+      desc.SetColorAttachments({res->indirectLight.imageViewProxy->Id()})
+          .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                           res->depthStencil.imageViewProxy->Id()})
+          .SetRenderAreaExtent(viewportExtent)
+          .SetProfilerInfo(Colors::sunFlower, "IndirectLightPass");
+      if (packedGather) desc.SetStorageBuffers({res->gatherScratch->Id()});
+      desc.SetRecordFunc([this, passData, giFlags, packedGather, fillIndirectData, rowsOf](RenderGraph::RenderPassContext passContext) {
+        auto shaderDataBuffer = fillIndirectData(passData);
+        ViewportResources *r = this->viewportResources.get();
+        const lgcu_image *light = passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc();     // "blurredDirectLightSampler"
+        const lgcu_image *moments = passContext.GetImageView(r->blurredDepthMoments.imageViewProxy->Id())->GetDesc();  // "blurredDepthMomentsSampler"
+        const lgcu_image *normal = passContext.GetImageView(r->normal.imageViewProxy->Id())->GetDesc();                // "normalSampler"
+        const lgcu_image *depth = passContext.GetImageView(r->depthStencil.imageViewProxy->Id())->GetDesc();           // "depthStencilSampler"
+        if (packedGather) {
+          Buffer *scratch = passContext.GetBuffer(r->gatherScratch->Id());
+          LgcuCheck(lgcu_gi_gather_packed(shaderDataBuffer, light, moments, normal, depth, passContext.GetColorAttachment(0)->GetDesc(), scratch->GetHandle(),
+                                          scratch->GetSize(), rowsOf(passData), passContext.GetStream()),
+                    "IndirectLightPass");
+        } else {
+          LgcuCheck(lgcu_gi_gather(shaderDataBuffer, light, moments, normal, depth, passContext.GetColorAttachment(0)->GetDesc(), giFlags, rowsOf(passData),
+                                   passContext.GetStream()),
+                    "IndirectLightPass");
+        }
+      });
+      graph->AddPass(desc);
+    }
 
     const int denoiserRadius = options.denoiserRadius;
     auto fillDenoiserData = [this, denoiserRadius](const PassData &pd) {
@@ -349,7 +387,9 @@ public:
           blurredDirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
           shadowMap(renderGraph, vk::Format::eD32Sfloat, glm::uvec2(1024, 1024), depthImageUsage),
           indirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
-          denoisedIndirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage) {}
+          denoisedIndirectLight(renderGraph, vk::Format::eR16G16B16A16Sfloat, screenSize, colorImageUsage),
+          gatherScratch(renderGraph->AddBuffer<GatherQuad>(uint32_t(lgcu_gather_scratch_bytes(screenSize.x, screenSize.y, 10) / sizeof(GatherQuad)))) {}
+    struct GatherQuad { float tap[4]; };
     UnmippedProxy albedo;
     UnmippedProxy emissive;
     UnmippedProxy normal;
@@ -361,6 +401,7 @@ public:
     UnmippedProxy shadowMap;
     UnmippedProxy indirectLight;
     UnmippedProxy denoisedIndirectLight;
+    RenderGraph::BufferProxyUnique gatherScratch; // transient: quad-packed depth pyramid of the GI gather (lgcu_gi_gather_pack)
   };
   ViewportResources *GetViewportResources() { return viewportResources.get(); }
   vk::Extent2D GetViewportExtent() const { return viewportExtent; }

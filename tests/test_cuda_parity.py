@@ -112,31 +112,67 @@ def test_mip_blur_chain_fused_equals_passes(cu, size):
             H.assert_bit_exact(hd, getattr(ref, dst), l, dst)
 
 
-@pytest.mark.parametrize("flags", [abi.GI_STRICT, abi.GI_DEFAULT], ids=["strict", "fast"])
+GATHER_MODES = ["strict", "fast", "packed"]
+
+
+def _gather(cu, p, dev, mode, rows=None):
+    """K5 through the C ABI: strict = shader-order kernel, fast = throughput kernel on the plain pyramids, packed = throughput
+    kernel on the quad-packed depth pyramid (lgcu_gi_gather_pack + lgcu_gi_gather_packed)."""
+    import torch
+
+    args = (C.byref(p.indirect), _v(dev.blurredDirectLight), _v(dev.blurredDepthMoments), _v(dev.normal), _v(dev.depthStencil), _v(dev.indirectLight))
+    r = None if rows is None else C.byref(abi.LgcuRows(*rows))
+    if mode == "packed":
+        need = cu.lib.lgcu_gather_scratch_bytes(dev.width, dev.height, passes.MIPS)
+        scratch = torch.full((need,), 0xCD, dtype=torch.uint8, device="cuda:0")
+        cu.gi_gather_pack(*args, scratch.data_ptr(), need, r)
+        cu.gi_gather_packed(*args, scratch.data_ptr(), need, r)
+        torch.cuda.synchronize()
+    else:
+        cu.gi_gather(*args, abi.GI_STRICT if mode == "strict" else abi.GI_DEFAULT, r)
+
+
+@pytest.mark.parametrize("mode", GATHER_MODES)
 @pytest.mark.parametrize("size", SIZES)
-def test_gi_gather_fp32_radiance(cu, size, flags):
+def test_gi_gather_fp32_radiance(cu, size, mode):
     """Un-quantised fp32 radiance (RGBA32F target) against the oracle: max-abs 1e-3 / PSNR >= 60 dB."""
     W, Hh = size
     sc, p, ref = H.oracle_frame(11, W, Hh, indirect_format=abi.FORMAT_R32G32B32A32_SFLOAT)
     dev = H.device_frame_like(ref, copy=("blurredDirectLight", "blurredDepthMoments", "normal", "depthStencil"))
-    cu.gi_gather(C.byref(p.indirect), _v(dev.blurredDirectLight), _v(dev.blurredDepthMoments), _v(dev.normal), _v(dev.depthStencil),
-                 _v(dev.indirectLight), flags, None)
+    _gather(cu, p, dev, mode)
     _sync()
     r = H.compare_level(dev.indirectLight.to_host(), ref.indirectLight, 0)
-    print("gi_gather", size, "strict" if flags else "fast", r)
+    print("gi_gather", size, mode, r)
     assert r["psnr"] >= 60.0, r
     assert r["outside_tol"] <= 1e-4 * r["texels"], r
 
 
-@pytest.mark.parametrize("flags", [abi.GI_STRICT, abi.GI_DEFAULT], ids=["strict", "fast"])
-def test_gi_gather_fp16_target(cu, flags):
+@pytest.mark.parametrize("mode", GATHER_MODES)
+def test_gi_gather_fp16_target(cu, mode):
     W, Hh = 640, 360
     sc, p, ref = H.oracle_frame(11, W, Hh)
     dev = H.device_frame_like(ref, copy=("blurredDirectLight", "blurredDepthMoments", "normal", "depthStencil"))
-    cu.gi_gather(C.byref(p.indirect), _v(dev.blurredDirectLight), _v(dev.blurredDepthMoments), _v(dev.normal), _v(dev.depthStencil),
-                 _v(dev.indirectLight), flags, None)
+    _gather(cu, p, dev, mode)
     _sync()
     H.assert_close(dev.indirectLight.to_host(), ref.indirectLight, 0, "indirectLight")
+
+
+@pytest.mark.parametrize("mode", ["fast", "packed"])
+def test_gi_gather_1080p_and_row_strips(cu, mode):
+    """Full-size frame (1920x1080, 8 march steps, LOD clamp at the top level) and the lgcu_rows contract: strips that do not
+    start on a multiple of 4 rows or of the 64-row tile reproduce the whole-frame result bit for bit."""
+    W, Hh = 1920, 1080
+    sc, p, ref = H.oracle_frame(12, W, Hh)
+    dev = H.device_frame_like(ref, copy=("blurredDirectLight", "blurredDepthMoments", "normal", "depthStencil"))
+    _gather(cu, p, dev, mode)
+    _sync()
+    whole = dev.indirectLight.to_host()
+    H.assert_close(whole, ref.indirectLight, 0, "indirectLight")
+    dev.indirectLight.tensor.fill_(0xCD)
+    for rows in ((0, 130), (130, 131), (131, 777), (777, 1080)):
+        _gather(cu, p, dev, mode, rows=rows)
+    _sync()
+    H.assert_bit_exact(dev.indirectLight.to_host(), whole, 0, "indirectLight strips vs whole")
 
 
 @pytest.mark.parametrize("radius", [0, 2])
@@ -201,15 +237,16 @@ def test_full_frame_chained(cu):
     assert (np.abs(a - b) > 1).mean() < 1e-3
 
 
-@pytest.mark.parametrize("flags", [abi.GI_STRICT, abi.GI_DEFAULT], ids=["strict", "fast"])
+@pytest.mark.parametrize("mode", GATHER_MODES)
 @pytest.mark.parametrize("name", H.GOLDEN_NAMES)
-def test_frame_vs_reference_golden_fixture(cu, name, flags):
+def test_frame_vs_reference_golden_fixture(cu, name, mode):
     """CUDA frame from the committed fixture's inputs vs the images the REFERENCE's own SPIR-V passes produced from them
     (tests/golden/make_golden.py). Integer/index work bit-exact, radiance within the north-star tolerance."""
     sc, p, ref, radius = H.load_golden(name)
     dev = H.device_frame_like(ref)
     inp = passes.upload_inputs(dev, sc)
-    passes.run_pass_list(cu, dev, p, inp, gi_flags=flags, stop_after="gather")
+    passes.run_pass_list(cu, dev, p, inp, stop_after="blur")
+    _gather(cu, p, dev, mode)
     _sync()
     levels = passes.mip_levels_built(sc.width, sc.height)
     for iname in ("normal", "depthMoments", "depthStencil"):
