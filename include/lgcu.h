@@ -201,6 +201,26 @@ int lgcu_gbuffer_direct_light(const lgcu_gbuffer_builder_data *gparams, const lg
 int lgcu_mip_blur_chain(const lgcu_image *chain, const lgcu_image *blurred, int32_t radius, const lgcu_rows *rows,
                         void *stream);
 
+/* The fused frame front: K1 + K2 + the radius-0 blur passes of level 0 + mip levels 1..LGCU_FRONT_MIP_LEVELS of both chains, in
+ * one pass over the fragments. Writes everything lgcu_gbuffer_direct_light writes, plus blurredDirectLight / blurredDepthMoments
+ * level 0 (= directLight / depthMoments level 0) and levels 1..4 of directLight and depthMoments. The four chain arguments are
+ * whole-image views (MippedProxy::imageViewProxy). A row strip must start on a multiple of 16 rows and end on one (or at the image
+ * bottom). Follow it with lgcu_frame_chains. */
+#define LGCU_FRONT_MIP_LEVELS 4
+int lgcu_frame_front(const lgcu_gbuffer_builder_data *gparams, const lgcu_direct_lighting_data *lparams,
+                     const lgcu_draw_call_data *objects, uint32_t nObjects, const lgcu_fragment *fragments,
+                     uint64_t fragmentPitchBytes, const lgcu_clear_values *clear, const lgcu_image *albedo,
+                     const lgcu_image *emissive, const lgcu_image *normal, const lgcu_image *depthMoments,
+                     const lgcu_image *depthStencil, const lgcu_image *shadowMap, const lgcu_image *directLight,
+                     const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments, const lgcu_rows *rows,
+                     void *stream);
+
+/* The rest of K3 + K4 after lgcu_frame_front, in one launch: blur (radius) of levels >= 1 of both chains and mip levels above
+ * LGCU_FRONT_MIP_LEVELS (built and blurred by one CTA per chain). With a row strip, the blur reads up to `radius` rows of each
+ * level outside the strip (they must be present) and the levels above LGCU_FRONT_MIP_LEVELS are built whole from level 4. */
+int lgcu_frame_chains(const lgcu_image *directLight, const lgcu_image *blurredDirectLight, const lgcu_image *depthMoments,
+                      const lgcu_image *blurredDepthMoments, int32_t radius, const lgcu_rows *rows, void *stream);
+
 /* K6(radius 0)+K7: denoised = noisy; swapchain = directLight + denoised * albedo. */
 int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_final_gatherer_data *fparams,
                               const lgcu_image *noisy, const lgcu_image *normal, const lgcu_image *depthMoments,

@@ -27,6 +27,7 @@ NVCC_COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ff
 CUDA_UNITS = {
     "k_streaming.cu": ["-fmad=false"],
     "k_chain.cu": ["-fmad=false"],
+    "k_front.cu": ["-fmad=false"],
     "k_gather_strict.cu": ["-fmad=false"],
     "k_gather_fast.cu": [],
     "lgcu_api.cu": ["-fmad=false"],

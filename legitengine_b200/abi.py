@@ -127,6 +127,8 @@ FUSED_SIGNATURES = {
     "gbuffer_direct_light": [P(GBufferBuilderData), P(DirectLightingData), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, P(ClearValues), IMG, IMG, IMG, IMG, IMG, IMG, IMG, ROWS],
     "mip_blur_chain": [IMG, IMG, C.c_int32, ROWS],
     "denoise_final_gather": [P(DenoiserData), P(FinalGathererData), IMG, IMG, IMG, IMG, IMG, IMG, IMG, IMG, ROWS],
+    "frame_front": [P(GBufferBuilderData), P(DirectLightingData), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, P(ClearValues), IMG, IMG, IMG, IMG, IMG, IMG, IMG, IMG, IMG, ROWS],
+    "frame_chains": [IMG, IMG, IMG, IMG, C.c_int32, ROWS],
     "gi_gather_pack": [P(IndirectLightingData), IMG, IMG, IMG, IMG, IMG, C.c_void_p, C.c_uint64, ROWS],
     "gi_gather_packed": [P(IndirectLightingData), IMG, IMG, IMG, IMG, IMG, C.c_void_p, C.c_uint64, ROWS],
 }

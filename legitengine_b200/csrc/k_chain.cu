@@ -37,3 +37,147 @@ cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s) {
 }
 
 } // namespace lgcu
+
+// ---------------------------------------------------------------------------------------------------------------------
+// frameChainsKernel — what remains of K3 + K4 after the frame-front kernel (k_front.cu), in ONE launch:
+//   grid part : blurLayerBuilder (radius 2, SH/Common/blurLayerBuilder.frag:17-35) of levels 1..gridLevels of both chains;
+//   tail part : one CTA per chain builds mip levels gridLevels+1..9 (mipLevelBuilder.frag:17-28) and blurs them. These
+//               levels hold < 2 % of the texels; walking them in one CTA replaces 20 launch-latency-bound launches.
+// Blur: a thread produces four vertically adjacent output texels of one column from a 4 x 7 register window (28 loads
+// instead of 64), each output summed in the shader's order (x outer, y inner, sequential fp32) so the result is bit-exact.
+namespace lgcu {
+namespace {
+
+constexpr uint32_t kF16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, kRG32 = LGCU_FORMAT_R32G32_SFLOAT;
+constexpr int kBlurTileW = 32, kBlurTileH = 32, kChainThreads = 256, kBlurRowsPerThread = 4;
+
+struct ChainsLaunch {
+  ChainsArgs a;
+  int blockBegin[2][kFrontMipLevels + 1]; // first CTA of (chain, level - 1); [..][gridLevels] = end
+  int rowBegin[kFrontMipLevels], rowEnd[kFrontMipLevels];
+  int tailBlocks; // 0 or 2
+};
+
+template <bool kCoherent> __device__ __forceinline__ uint2 loadTexel(const LevelView &l, int x, int y) {
+  const uint2 *p = reinterpret_cast<const uint2 *>(l.ptr + (size_t)y * l.pitch) + x;
+  return kCoherent ? __ldcg(p) : __ldg(p);
+}
+
+// blurLayerBuilder.frag:20-31 for the outputs (x, y..y+rows-1) of one column
+template <uint32_t F, int R, bool kCoherent>
+__device__ __forceinline__ void blurColumn(const LevelView &src, const LevelView &dst, int x, int y, int rows) {
+  constexpr int kWin = 2 * R, kSpan = kBlurRowsPerThread + kWin - 1;
+  uint2 t[kWin][kSpan];
+#pragma unroll
+  for (int i = 0; i < kWin; i++) {
+    const int sx = clampi(x + i - R, 0, src.w - 1);
+#pragma unroll
+    for (int j = 0; j < kSpan; j++) t[i][j] = loadTexel<kCoherent>(src, sx, clampi(y + j - R, 0, src.h - 1));
+  }
+#pragma unroll
+  for (int o = 0; o < kBlurRowsPerThread; o++) {
+    if (o >= rows) break;
+    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float totalWeight = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kWin; i++)
+#pragma unroll
+      for (int j = 0; j < kWin; j++) {
+        const float4 v = Texel<F>::unpack(t[i][o + j]);
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        totalWeight += 1.0f;
+      }
+    Texel<F>::store(dst, x, y + o, make_float4(sum.x / totalWeight, sum.y / totalWeight, sum.z / totalWeight, sum.w / totalWeight));
+  }
+}
+
+template <uint32_t F, bool kCoherent> __device__ __forceinline__ void blurColumnR(int radius, const LevelView &src, const LevelView &dst, int x, int y, int rows) {
+  if (radius == 2)
+    blurColumn<F, 2, kCoherent>(src, dst, x, y, rows);
+  else
+    blurColumn<F, 1, kCoherent>(src, dst, x, y, rows);
+}
+
+template <uint32_t F> __device__ __forceinline__ void mipTexel(const LevelView &src, const LevelView &dst, int x, int y) {
+  const uint4 top = __ldcg(reinterpret_cast<const uint4 *>(src.ptr + (size_t)(2 * y) * src.pitch) + x);
+  const uint4 bot = __ldcg(reinterpret_cast<const uint4 *>(src.ptr + (size_t)(2 * y + 1) * src.pitch) + x);
+  const float4 s00 = Texel<F>::unpack(make_uint2(top.x, top.y)), s10 = Texel<F>::unpack(make_uint2(top.z, top.w));
+  const float4 s01 = Texel<F>::unpack(make_uint2(bot.x, bot.y)), s11 = Texel<F>::unpack(make_uint2(bot.z, bot.w));
+  float4 sum;
+  sum.x = ((((0.0f + s00.x) + s10.x) + s01.x) + s11.x) / 4.0f;
+  sum.y = ((((0.0f + s00.y) + s10.y) + s01.y) + s11.y) / 4.0f;
+  sum.z = ((((0.0f + s00.z) + s10.z) + s01.z) + s11.z) / 4.0f;
+  sum.w = ((((0.0f + s00.w) + s10.w) + s01.w) + s11.w) / 4.0f;
+  Texel<F>::store(dst, x, y, sum);
+}
+
+template <uint32_t F> __device__ void chainTail(const ChainsArgs &a, const PyramidView &chain, const PyramidView &blurred) {
+  // mip levels one after the other (each reads the level just written by this CTA), then their blurs
+  for (int l = a.gridLevels + 1; l < a.levels; l++) {
+    const LevelView &src = chain.lv[l - 1], &dst = chain.lv[l];
+    for (int i = threadIdx.x; i < dst.w * dst.h; i += kChainThreads) mipTexel<F>(src, dst, i % dst.w, i / dst.w);
+    __syncthreads();
+  }
+  for (int l = a.gridLevels + 1; l < a.levels; l++) {
+    const LevelView &src = chain.lv[l], &dst = blurred.lv[l];
+    const int groups = (src.h + kBlurRowsPerThread - 1) / kBlurRowsPerThread;
+    for (int i = threadIdx.x; i < src.w * groups; i += kChainThreads) {
+      const int x = i % src.w, y = (i / src.w) * kBlurRowsPerThread;
+      blurColumnR<F, true>(a.radius, src, dst, x, y, min(kBlurRowsPerThread, src.h - y));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_constant__ ChainsLaunch p) {
+  const ChainsArgs &a = p.a;
+  int b = blockIdx.x;
+  if (b < p.tailBlocks) {
+    if (b == 0)
+      chainTail<kF16>(a, a.light, a.blurredLight);
+    else
+      chainTail<kRG32>(a, a.moments, a.blurredMoments);
+    return;
+  }
+  b -= p.tailBlocks;
+  const int chain = b >= p.blockBegin[1][0] ? 1 : 0;
+  int l = 1;
+  while (l < a.gridLevels && b >= p.blockBegin[chain][l]) l++; // level l occupies [blockBegin[l-1], blockBegin[l])
+  b -= p.blockBegin[chain][l - 1];
+  const LevelView &src = chain ? a.moments.lv[l] : a.light.lv[l], &dst = chain ? a.blurredMoments.lv[l] : a.blurredLight.lv[l];
+  const int bx = (src.w + kBlurTileW - 1) / kBlurTileW;
+  const int x = (b % bx) * kBlurTileW + (threadIdx.x & 31);
+  const int y = p.rowBegin[l - 1] + (b / bx) * kBlurTileH + (threadIdx.x >> 5) * kBlurRowsPerThread;
+  if (x >= src.w || y >= p.rowEnd[l - 1]) return;
+  const int rows = min(kBlurRowsPerThread, p.rowEnd[l - 1] - y);
+  if (chain)
+    blurColumnR<kRG32, false>(a.radius, src, dst, x, y, rows);
+  else
+    blurColumnR<kF16, false>(a.radius, src, dst, x, y, rows);
+}
+
+} // namespace
+
+cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s) {
+  ChainsLaunch p;
+  p.a = a;
+  int blocks = 0;
+  for (int chain = 0; chain < 2; chain++) {
+    for (int l = 1; l <= a.gridLevels; l++) {
+      const LevelView &lv = a.light.lv[l];
+      const int y0 = a.rows.y0 >> l, y1 = (a.rows.y1 + ((1 << l) - 1)) >> l;
+      p.rowBegin[l - 1] = y0 < lv.h ? y0 : lv.h;
+      p.rowEnd[l - 1] = y1 < lv.h ? y1 : lv.h;
+      p.blockBegin[chain][l - 1] = blocks;
+      const int rows = p.rowEnd[l - 1] - p.rowBegin[l - 1];
+      if (rows > 0) blocks += ((lv.w + kBlurTileW - 1) / kBlurTileW) * ((rows + kBlurTileH - 1) / kBlurTileH);
+    }
+    p.blockBegin[chain][a.gridLevels] = blocks;
+  }
+  if (a.gridLevels == 0) p.blockBegin[1][0] = 0x7fffffff;
+  p.tailBlocks = a.levels > a.gridLevels + 1 ? 2 : 0;
+  if (blocks + p.tailBlocks == 0) return cudaSuccess;
+  frameChainsKernel<<<blocks + p.tailBlocks, kChainThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+} // namespace lgcu

@@ -383,6 +383,83 @@ int lgcu_mip_blur_chain(const lgcu_image *chain, const lgcu_image *blurred, int3
   return cudaStatus(launchMipBlurChain(a, static_cast<cudaStream_t>(stream)), "mip_blur_chain");
 }
 
+// ------------------------------------------------------------------------------------------------------- frame front / chains
+static int smCountOfCurrentDevice() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  return sms;
+}
+
+static int builtLevels(const lgcu_image *img) { // MipBuilder::BuildMips stops at the first level with a zero dimension (MipBuilder.h:151-152)
+  int levels = 1;
+  for (uint32_t l = 1; l < img->mipCount; l++) {
+    if ((img->width >> l) == 0 || (img->height >> l) == 0) break;
+    levels++;
+  }
+  return levels;
+}
+
+static bool wholeChain(const lgcu_image *img, uint32_t format, const lgcu_image *like, const char *name, int *st) {
+  if (!expectFormat(img, format, name, st)) return false;
+  if (img->baseMip != 0 || img->mipCount == 0 || img->mipCount > (uint32_t)kMaxGatherLevels || (like && (img->width != like->width || img->height != like->height || img->mipCount != like->mipCount))) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "%s: must be a whole-image view of the chain (same size and level count as its partner)", name);
+    return false;
+  }
+  return true;
+}
+
+int lgcu_frame_front(const lgcu_gbuffer_builder_data *gparams, const lgcu_direct_lighting_data *lparams, const lgcu_draw_call_data *objects,
+                     uint32_t nObjects, const lgcu_fragment *fragments, uint64_t fragmentPitchBytes, const lgcu_clear_values *clear,
+                     const lgcu_image *albedo, const lgcu_image *emissive, const lgcu_image *normal, const lgcu_image *depthMoments,
+                     const lgcu_image *depthStencil, const lgcu_image *shadowMap, const lgcu_image *directLight, const lgcu_image *blurredDirectLight,
+                     const lgcu_image *blurredDepthMoments, const lgcu_rows *rows, void *stream) {
+  FrontArgs a;
+  int st = LGCU_OK;
+  if (!wholeChain(directLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, nullptr, "directLight", &st) ||
+      !wholeChain(blurredDirectLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, directLight, "blurredDirectLight", &st) ||
+      !wholeChain(depthMoments, LGCU_FORMAT_R32G32_SFLOAT, directLight, "depthMoments", &st) ||
+      !wholeChain(blurredDepthMoments, LGCU_FORMAT_R32G32_SFLOAT, directLight, "blurredDepthMoments", &st))
+    return st;
+  if (!fillGBufferArgs(gparams, objects, nObjects, fragments, fragmentPitchBytes, clear, albedo, emissive, normal, depthMoments, depthStencil, rows, &a.g, &st))
+    return st;
+  if (!fillDirectLightArgs(lparams, albedo, emissive, normal, depthStencil, shadowMap, directLight, rows, &a.l, &st)) return st;
+  if (!resolveLevel(blurredDirectLight, 0, "blurredDirectLight", &a.blurLight0, &st) || !resolveLevel(blurredDepthMoments, 0, "blurredDepthMoments", &a.blurMoments0, &st))
+    return st;
+  if (!sameSize(a.g.albedo, a.blurLight0, "albedo", "blurredDirectLight", &st)) return st;
+  if ((a.g.rows.y0 % 16) != 0 || ((a.g.rows.y1 % 16) != 0 && a.g.rows.y1 != a.g.albedo.h))
+    return fail(LGCU_ERR_INVALID_ARGUMENT, "frame_front: row strip [%d,%d) must start and end on multiples of 16 rows", a.g.rows.y0, a.g.rows.y1);
+  const int levels = builtLevels(directLight);
+  a.mipLevels = levels - 1 < kFrontMipLevels ? levels - 1 : kFrontMipLevels;
+  for (int l = 1; l <= kFrontMipLevels; l++) {
+    const uint32_t lod = l <= a.mipLevels ? (uint32_t)l : 0u;
+    if (!resolveLevel(directLight, lod, "directLight", &a.lightMip[l - 1], &st) || !resolveLevel(depthMoments, lod, "depthMoments", &a.momentsMip[l - 1], &st)) return st;
+  }
+  return cudaStatus(launchFrameFront(a, smCountOfCurrentDevice(), static_cast<cudaStream_t>(stream)), "frame_front");
+}
+
+int lgcu_frame_chains(const lgcu_image *directLight, const lgcu_image *blurredDirectLight, const lgcu_image *depthMoments,
+                      const lgcu_image *blurredDepthMoments, int32_t radius, const lgcu_rows *rows, void *stream) {
+  ChainsArgs a;
+  int st = LGCU_OK;
+  if (!wholeChain(directLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, nullptr, "directLight", &st) ||
+      !wholeChain(blurredDirectLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, directLight, "blurredDirectLight", &st) ||
+      !wholeChain(depthMoments, LGCU_FORMAT_R32G32_SFLOAT, directLight, "depthMoments", &st) ||
+      !wholeChain(blurredDepthMoments, LGCU_FORMAT_R32G32_SFLOAT, directLight, "blurredDepthMoments", &st))
+    return st;
+  if (radius < 1 || radius > 2) return fail(LGCU_ERR_UNSUPPORTED, "frame_chains: radius %d (the reference uses 2)", radius);
+  if (!resolvePyramid(directLight, "directLight", &a.light, &st) || !resolvePyramid(blurredDirectLight, "blurredDirectLight", &a.blurredLight, &st) ||
+      !resolvePyramid(depthMoments, "depthMoments", &a.moments, &st) || !resolvePyramid(blurredDepthMoments, "blurredDepthMoments", &a.blurredMoments, &st))
+    return st;
+  for (int l = 0; l < a.light.count; l++)
+    if (a.light.lv[l].pitch != a.blurredLight.lv[l].pitch || a.moments.lv[l].pitch != a.blurredMoments.lv[l].pitch || a.light.lv[l].w != a.moments.lv[l].w)
+      return fail(LGCU_ERR_INVALID_ARGUMENT, "frame_chains: the four chains must share one layout");
+  a.levels = builtLevels(directLight);
+  a.radius = radius;
+  a.gridLevels = a.levels - 1 < kFrontMipLevels ? a.levels - 1 : kFrontMipLevels;
+  a.rows = rowRange(rows, 0, (int)directLight->height);
+  return cudaStatus(launchFrameChains(a, static_cast<cudaStream_t>(stream)), "frame_chains");
+}
+
 // ------------------------------------------------------------------------------------------------------- K5
 static bool fillGatherArgs(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
                            const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, const lgcu_rows *rows, GatherArgs *a,

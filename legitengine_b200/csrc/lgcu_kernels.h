@@ -103,6 +103,27 @@ struct GBufferLightArgs { // fused K1 + K2
   DirectLightArgs l;
 };
 
+constexpr int kFrontMipLevels = 4; // mip levels 1..4 are built inside the frame-front kernel's 64x16 tiles
+
+struct FrontArgs { // fused K1 + K2 + level-0 blur copies + mip levels 1..kFrontMipLevels of both chains
+  GBufferArgs g;
+  DirectLightArgs l;
+  LevelView blurLight0, blurMoments0;
+  LevelView lightMip[kFrontMipLevels], momentsMip[kFrontMipLevels]; // levels 1..4
+  int mipLevels;                                                    // how many of them exist (0..4)
+  int tilesX, tilesY, tileCount;                                    // filled by the launcher
+};
+
+struct ChainsArgs { // everything of K3 + K4 that the front kernel leaves: blur of levels >= 1, mips above kFrontMipLevels
+  PyramidView light, blurredLight, moments, blurredMoments;
+  int levels;     // levels present in the chains
+  int radius;     // blur radius of levels >= 1 (1 or 2)
+  int gridLevels; // levels 1..gridLevels are blurred by the grid (they were built by the front kernel)
+  RowRange rows;  // base rows
+};
+
+cudaError_t launchFrameFront(const FrontArgs &a, int smCount, cudaStream_t s);
+cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s);
 cudaError_t launchGBufferResolve(const GBufferArgs &a, cudaStream_t s);
 cudaError_t launchDirectLight(const DirectLightArgs &a, cudaStream_t s);
 cudaError_t launchGBufferDirectLight(const GBufferLightArgs &a, cudaStream_t s);

@@ -10,8 +10,9 @@
 //    hot path, so the scene arrives already rasterised: a per-pixel fragment buffer, the
 //    per-draw-call constants and the light's depth map. "ShadowPass" copies that depth map into the shadowMap image;
 //    "GBufferPass" runs the fragment stage (lgcu_gbuffer_resolve) over the fragment buffer.
-//  * FrameOptions::mode == Fused replaces groups of passes by the fused entry points (K1+K2, mip+blur chain, K6+K7):
-//    identical images, fewer trips through HBM. PassGranular is the 1:1 pass list (47 passes incl. shadow).
+//  * FrameOptions::mode == Fused replaces groups of passes by the fused entry points (frame front = K1+K2+level-0 blur+mips 1..4,
+//    frame chains = remaining blur/mip work, packed GI gather, K6+K7): identical images, 6 launches instead of 46 passes.
+//    PassGranular is the 1:1 pass list (47 passes incl. shadow).
 //  * The debug overlay (DebugRenderer, :344-350) is out of scope.
 #pragma once
 
@@ -183,7 +184,50 @@ public:
       for (uint32_t mipLevel = 0; mipLevel < res->blurredDirectLight.mipImageViewProxies.size(); mipLevel++)
         blurBuilder.ApplyBlur(graph, frameInfo.memoryPool, res->depthMoments.mipImageViewProxies[mipLevel]->Id(),
                               res->blurredDepthMoments.mipImageViewProxies[mipLevel]->Id(), mipLevel == 0 ? 0 : 2);
+    } else if (!useRows || (options.rows.y0 % 16 == 0 && (options.rows.y1 % 16 == 0 || options.rows.y1 == viewportExtent.height))) {
+      // K1 + K2 + level-0 blur copies + mip levels 1..4 of both chains in one pass over the fragments (lgcu_frame_front), then the
+      // remaining blur / mip work of both chains in one launch (lgcu_frame_chains): 2 kernels for 41 reference passes (:106-221)
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetColorAttachments({res->albedo.imageViewProxy->Id(), res->emissive.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
+                                               res->depthMoments.imageViewProxy->Id(), res->directLight.imageViewProxy->Id(),
+                                               res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id()},
+                                              vk::AttachmentLoadOp::eClear)
+                         .SetDepthAttachment(res->depthStencil.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
+                         .SetInputImages({res->shadowMap.imageViewProxy->Id()})
+                         .SetStorageBuffers({scene->fragmentsProxy->Id(), scene->objectsProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::belizeHole, "FrameFrontPass")
+                         .SetRecordFunc([this, passData, fillGBufferData, fillLightData, clearOf, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           auto gbufferData = fillGBufferData(passData);
+                           auto lightData = fillLightData(passData);
+                           const lgcu_clear_values clear = clearOf(passContext);
+                           Scene *sc = passData.scene;
+                           LgcuCheck(lgcu_frame_front(gbufferData, lightData, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
+                                                      sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
+                                                      sc->fragmentPitch, &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
+                                                      passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(),
+                                                      passContext.GetDepthAttachment()->GetDesc(),
+                                                      passContext.GetImageView(this->viewportResources->shadowMap.imageViewProxy->Id())->GetDesc(),
+                                                      passContext.GetColorAttachment(4)->GetDesc(), passContext.GetColorAttachment(5)->GetDesc(),
+                                                      passContext.GetColorAttachment(6)->GetDesc(), rowsOf(passData), passContext.GetStream()),
+                                     "FrameFrontPass");
+                         }));
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetStorageImages({res->directLight.imageViewProxy->Id(), res->blurredDirectLight.imageViewProxy->Id(), res->depthMoments.imageViewProxy->Id(),
+                                            res->blurredDepthMoments.imageViewProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::nephritis, "FrameChainsPass")
+                         .SetRecordFunc([this, passData, rowsOf](RenderGraph::RenderPassContext passContext) {
+                           ViewportResources *r = this->viewportResources.get();
+                           LgcuCheck(lgcu_frame_chains(passContext.GetImageView(r->directLight.imageViewProxy->Id())->GetDesc(),
+                                                       passContext.GetImageView(r->blurredDirectLight.imageViewProxy->Id())->GetDesc(),
+                                                       passContext.GetImageView(r->depthMoments.imageViewProxy->Id())->GetDesc(),
+                                                       passContext.GetImageView(r->blurredDepthMoments.imageViewProxy->Id())->GetDesc(), 2, rowsOf(passData),
+                                                       passContext.GetStream()),
+                                     "FrameChainsPass");
+                         }));
     } else {
+      // row strips that do not sit on the 16-row tile grid of the frame-front kernel: K1+K2 and one chain call per MippedProxy
       // K1 + K2 fused: everything GBufferPass and LightPass write, from one read of the fragments
       graph->AddPass(RenderGraph::RenderPassDesc()
                          .SetColorAttachments({res->albedo.imageViewProxy->Id(), res->emissive.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),

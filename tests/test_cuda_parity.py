@@ -112,6 +112,76 @@ def test_mip_blur_chain_fused_equals_passes(cu, size):
             H.assert_bit_exact(hd, getattr(ref, dst), l, dst)
 
 
+def _frame_front(cu, p, dev, inp, rows=None):
+    r = None if rows is None else C.byref(abi.LgcuRows(*rows))
+    cu.frame_front(C.byref(p.gbuffer), C.byref(p.light), inp["objects_ptr"], inp["n_objects"], inp["fragments_ptr"], inp["pitch"], C.byref(p.clear),
+                   _v(dev.albedo), _v(dev.emissive), _v(dev.normal), _v(dev.depthMoments), _v(dev.depthStencil), _v(dev.shadowMap), _v(dev.directLight),
+                   _v(dev.blurredDirectLight), _v(dev.blurredDepthMoments), r)
+
+
+def _frame_chains(cu, dev, rows=None):
+    r = None if rows is None else C.byref(abi.LgcuRows(*rows))
+    cu.frame_chains(_v(dev.directLight), _v(dev.blurredDirectLight), _v(dev.depthMoments), _v(dev.blurredDepthMoments), 2, r)
+
+
+CHAIN_IMAGES = ("directLight", "blurredDirectLight", "depthMoments", "blurredDepthMoments")
+
+
+@pytest.mark.parametrize("size", SIZES + [(1920, 1080), (67, 35), (16, 16), (1, 1), (5, 300)])
+def test_frame_front_and_chains_equal_the_separate_passes(cu, size):
+    """lgcu_frame_front + lgcu_frame_chains (2 launches) against the 41 pass-granular CUDA launches they replace: every image
+    and every mip level bit for bit — ragged sizes (odd rows/columns dropped by the chain), sizes below one tile, 1x1."""
+    W, Hh = size
+    sc, p, ref = H.oracle_frame(17, W, Hh, n_boxes=32)
+    a = H.device_frame_like(ref)
+    inp_a = passes.upload_inputs(a, sc)
+    passes.run_pass_list(cu, a, p, inp_a, stop_after="blur")
+    b = H.device_frame_like(ref)
+    inp_b = passes.upload_inputs(b, sc)
+    _frame_front(cu, p, b, inp_b)
+    _frame_chains(cu, b)
+    _sync()
+    levels = passes.mip_levels_built(W, Hh)
+    for name in ("albedo", "emissive", "normal", "depthStencil"):
+        H.assert_bit_exact(b.__dict__[name].to_host(), a.__dict__[name].to_host(), 0, name)
+    for name in CHAIN_IMAGES:
+        ha, hb = getattr(a, name).to_host(), getattr(b, name).to_host()
+        for l in range(levels):
+            H.assert_bit_exact(hb, ha, l, name)
+    # and the moments chain against the oracle itself (exact-order fp32)
+    for l in range(levels):
+        H.assert_bit_exact(b.blurredDepthMoments.to_host(), ref.blurredDepthMoments, l, "blurredDepthMoments vs oracle")
+
+
+def test_frame_front_row_strips(cu):
+    """Strips on the 16-row grid, front then chains per strip (chains after all fronts: the blur reads neighbouring rows)."""
+    W, Hh = 250, 141
+    sc, p, ref = H.oracle_frame(17, W, Hh, n_boxes=32)
+    whole = H.device_frame_like(ref)
+    inp = passes.upload_inputs(whole, sc)
+    _frame_front(cu, p, whole, inp)
+    _frame_chains(cu, whole)
+    dev = H.device_frame_like(ref)
+    inp2 = passes.upload_inputs(dev, sc)
+    strips = ((0, 48), (48, 64), (64, 141))
+    for rows in strips:
+        _frame_front(cu, p, dev, inp2, rows=rows)
+    for rows in strips:
+        _frame_chains(cu, dev, rows=rows)
+    _sync()
+    levels = passes.mip_levels_built(W, Hh)
+    for name in CHAIN_IMAGES:
+        ha, hb = getattr(whole, name).to_host(), getattr(dev, name).to_host()
+        for l in range(levels):
+            H.assert_bit_exact(hb, ha, l, name)
+    lib = cu.lib
+    bad = abi.LgcuRows(8, 141)
+    st = lib.lgcu_frame_front(C.byref(p.gbuffer), C.byref(p.light), inp2["objects_ptr"], inp2["n_objects"], inp2["fragments_ptr"], inp2["pitch"], C.byref(p.clear),
+                              _v(dev.albedo), _v(dev.emissive), _v(dev.normal), _v(dev.depthMoments), _v(dev.depthStencil), _v(dev.shadowMap), _v(dev.directLight),
+                              _v(dev.blurredDirectLight), _v(dev.blurredDepthMoments), C.byref(bad), None)
+    assert st == abi.LGCU_ERR_INVALID_ARGUMENT
+
+
 GATHER_MODES = ["strict", "fast", "packed"]
 
 

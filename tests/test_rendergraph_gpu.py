@@ -83,7 +83,7 @@ def test_frame_vs_oracle_and_profile():
     r.sync()
     prof = r.profile()
     names = [n for n, _ in prof]
-    assert names == ["ShadowPass", "GBufferLightPass", "MipBlurChainPass", "MipBlurChainPass", "GatherPackPass", "IndirectLightPass", "DenoiseGatheringPass"], names
+    assert names == ["ShadowPass", "FrameFrontPass", "FrameChainsPass", "GatherPackPass", "IndirectLightPass", "DenoiseGatheringPass"], names
     assert all(ms >= 0 for _, ms in prof)
     for n in ("directLight", "blurredDirectLight", "indirectLight", "denoisedIndirectLight"):
         H.assert_close(r.download_image(n), getattr(ref, n), 0, n, max_outside_frac=1e-3)
