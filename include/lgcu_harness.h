@@ -43,6 +43,11 @@ int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t siz
  * profile != 0 records per-pass GPU events (read them with lgh_get_profile after lgh_sync). */
 int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile);
 
+/* Part of a fused frame: only the passes of the selected stages are declared and run. A multi-GPU strip renderer runs the stages
+ * one at a time and exchanges halo rows between them (legitengine_b200/multigpu.py). */
+enum { LGH_STAGE_FRONT = 1, LGH_STAGE_CHAINS = 2, LGH_STAGE_GATHER = 4, LGH_STAGE_FINAL = 8, LGH_STAGE_ALL = 15 };
+int lgh_render_stages(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t stages);
+
 /* Capture the same frame into a CUDA graph once (after at least one lgh_render_frame with the same arguments has
  * allocated the images), then replay it with a single launch per frame. */
 int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows);

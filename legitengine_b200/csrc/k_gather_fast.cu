@@ -26,6 +26,7 @@
 //    exactly as the shader does (its fp32 cancellation noise is part of the reference result and is amplified by
 //    1/sample distance), so the two variants see the same centre.
 #include <cmath>
+#include <cstdlib>
 
 #include "lgcu_kernels.h"
 
@@ -40,7 +41,7 @@ constexpr uint32_t F16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, D32 = LGCU_FORMAT_D32_
 constexpr float kFloorMagic = 12582912.0f; // 1.5 * 2^23: x + magic (rounded down) has floor(x) in its low mantissa bits
 constexpr int kFloorMagicBits = 0x4B400000;
 
-struct LevelGeom { // per pyramid level
+struct __align__(16) LevelGeom { // per pyramid level
   float scaleX, scaleY; // w_l / viewport.x, h_l / viewport.y
   float maxX, maxY;     // w_l - 1, h_l - 1
   int quadOfs, quadPitch; // level origin and row pitch of the quad-packed depth pyramid, in float4
@@ -48,12 +49,12 @@ struct LevelGeom { // per pyramid level
   int wm1, hm1;
   int pad0, pad1;
 };
-struct StepRow { // per (pattern, step): everything the march needs for one sample, in one uniform 112-byte row
+struct __align__(16) StepRow { // per (pattern, step): everything the march needs for one sample, in one uniform 112-byte row
   float off, frac;
   int l0, l1;
   LevelGeom g0, g1;
 };
-struct DirEntry { // per (pattern, direction)
+struct __align__(16) DirEntry { // per (pattern, direction)
   float dirX, dirY, invDirX, invDirY;
   float rdX, rdY, rdZ, q2; // Rd = Ra*dirX + Rb*dirY, q2 = |Rd|²
 };
@@ -156,9 +157,11 @@ __device__ __forceinline__ float4 mulMat4Exact(const Mat4 &M, float x, float y, 
 }
 __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 
-template <bool kQuads>
-__global__ void __launch_bounds__(kThreads, 4) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
-                                                                 const float4 *__restrict__ quads) {
+template <bool kQuads, bool kSmem, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
+                                                                          const float4 *__restrict__ quads) {
+  __shared__ StepRow sRows[kSmem ? kMaxSteps : 1];
+  __shared__ DirEntry sDir[kSmem ? kGatherDirs : 1];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
   const int tileX = blockIdx.x * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * kTile;
@@ -174,7 +177,16 @@ __global__ void __launch_bounds__(kThreads, 4) gatherFastKernel(const __grid_con
   for (int idx = 0; idx < 16; idx++) { // one pattern class per pass (CTA-uniform)
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
-    if (!__any_sync(0xffffffffu, active)) continue;
+    if (kSmem) { // this pass's table rows -> shared memory: the march then reads them with vector loads instead of LDCU + MOV
+      __syncthreads();
+      constexpr int kRowWords = kMaxSteps * (int)(sizeof(StepRow) / 4), kDirWords = kGatherDirs * (int)(sizeof(DirEntry) / 4);
+      const uint32_t *srcRows = reinterpret_cast<const uint32_t *>(&tb.row[idx * kMaxSteps]), *srcDir = reinterpret_cast<const uint32_t *>(&tb.dir[idx][0]);
+      for (int i = t; i < kRowWords; i += kThreads) reinterpret_cast<uint32_t *>(sRows)[i] = srcRows[i];
+      if (t < kDirWords) reinterpret_cast<uint32_t *>(sDir)[t] = srcDir[t];
+      __syncthreads();
+    } else if (!__any_sync(0xffffffffu, active)) {
+      continue;
+    }
     const int cx = active ? x : 0, cy = active ? y : a.rows.y0; // inactive lanes shade a valid pixel and discard it
     const float px = (float)cx + 0.5f, py = (float)cy + 0.5f;
     // --- centre reconstruction in the shader's order (:116-132, :182) -------------------------------------------------
@@ -194,11 +206,11 @@ __global__ void __launch_bounds__(kThreads, 4) gatherFastKernel(const __grid_con
     const float n0 = sqrtf(q0);
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
     float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
-    const StepRow *__restrict__ rows = &tb.row[idx * kMaxSteps];
+    const StepRow *__restrict__ rows = kSmem ? sRows : &tb.row[idx * kMaxSteps];
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
-      const DirEntry de = tb.dir[idx][d];
+      const DirEntry de = kSmem ? sDir[d] : tb.dir[idx][d];
       const V3 Rd = v3(de.rdX, de.rdY, de.rdZ);
       // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
       const float q2 = de.q2, q1 = 2.0f * dotf(R0, Rd);
@@ -434,7 +446,7 @@ cudaError_t launchGatherPack(const GatherArgs &a, void *scratch, cudaStream_t s)
   int blocks = 0;
   for (int l = 0; l < p.levels; l++) {
     // strip: the march reaches ~13 level-l texels beyond the strip; the coarse levels are rebuilt whole
-    const int reach = 16;
+    const int reach = 15; // quad row q reads moment rows q-1 and q: rows [strip-16, strip+16) of each level must be present (sharding.GATHER_REACH)
     int r0 = (a.rows.y0 >> l) - reach, r1 = ((a.rows.y1 + (1 << l) - 1) >> l) + reach + 1;
     const bool whole = l >= 6 || l == p.levels - 1; // the top level serves every clamped LOD
     if (whole || r0 < 0) r0 = 0;
@@ -455,10 +467,18 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   FastTables f;
   if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, &f, nullptr)) return launchGatherStrict(a, t, s);
   const dim3 grid((a.indirect.w + kTile - 1) / kTile, (a.rows.y1 - (a.rows.y0 & ~3) + kTile - 1) / kTile);
-  if (scratch)
-    gatherFastKernel<true><<<grid, kThreads, 0, s>>>(a, f, static_cast<const float4 *>(scratch));
+  static const int variant = getenv("LGCU_GATHER_VARIANT") ? atoi(getenv("LGCU_GATHER_VARIANT")) : 0; // development switch
+  const float4 *q = static_cast<const float4 *>(scratch);
+  if (!scratch)
+    gatherFastKernel<false, false, 4><<<grid, kThreads, 0, s>>>(a, f, nullptr);
+  else if (variant == 1)
+    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 2)
+    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 3)
+    gatherFastKernel<true, true, 3><<<grid, kThreads, 0, s>>>(a, f, q);
   else
-    gatherFastKernel<false><<<grid, kThreads, 0, s>>>(a, f, nullptr);
+    gatherFastKernel<true, false, 4><<<grid, kThreads, 0, s>>>(a, f, q);
   return cudaGetLastError();
 }
 

@@ -14,6 +14,7 @@ from . import abi, images
 
 MODE_PASS_GRANULAR = 0
 MODE_FUSED = 1
+STAGE_FRONT, STAGE_CHAINS, STAGE_GATHER, STAGE_FINAL, STAGE_ALL = 1, 2, 4, 8, 15
 
 IMAGE_NAMES = (
     "albedo", "emissive", "normal", "depthMoments", "blurredDepthMoments", "depthStencil", "directLight",
@@ -40,6 +41,7 @@ def load_harness() -> C.CDLL:
         lib.lgh_upload_objects.argtypes = [R, C.c_void_p, C.c_uint32]
         lib.lgh_upload_light_depth.argtypes = [R, C.c_void_p, C.c_uint32]
         lib.lgh_render_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
+        lib.lgh_render_stages.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         lib.lgh_capture_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS]
         lib.lgh_replay_frame.argtypes = [R]
         lib.lgh_captured_kernel_count.argtypes = [R]
@@ -108,6 +110,10 @@ class Renderer:
 
     def render_frame(self, mode: int = MODE_FUSED, denoiser_radius: int = 0, gi_flags: int = abi.GI_DEFAULT, rows=None, profile: bool = False) -> None:
         _check(self.lib.lgh_render_frame(self.handle, mode, denoiser_radius, gi_flags, self._rows(rows), 1 if profile else 0), "lgh_render_frame")
+
+    def render_stages(self, stages: int, rows=None, denoiser_radius: int = 0, gi_flags: int = abi.GI_DEFAULT) -> None:
+        """Selected stages of the fused frame (STAGE_* bits) on rows [y0, y1): the building block of the strip-sharded renderer."""
+        _check(self.lib.lgh_render_stages(self.handle, MODE_FUSED, denoiser_radius, gi_flags, self._rows(rows), stages), "lgh_render_stages")
 
     def capture_frame(self, mode: int = MODE_FUSED, denoiser_radius: int = 0, gi_flags: int = abi.GI_DEFAULT, rows=None) -> None:
         _check(self.lib.lgh_capture_frame(self.handle, mode, denoiser_radius, gi_flags, self._rows(rows)), "lgh_capture_frame")

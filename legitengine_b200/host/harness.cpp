@@ -70,7 +70,7 @@ struct lgh_renderer {
     scene->lightDepthSize = lightDepthSize;
   }
 
-  void declareAndExecute(uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, bool profile) {
+  void declareAndExecute(uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, bool profile, uint32_t stages = FrameOptions::StageAll) {
     ensureScene();
     memoryPool.MapBuffer();
     FrameInfo frameInfo;
@@ -80,6 +80,7 @@ struct lgh_renderer {
     options.mode = mode == LGH_MODE_PASS_GRANULAR ? FrameOptions::Mode::PassGranular : FrameOptions::Mode::Fused;
     options.denoiserRadius = denoiserRadius;
     options.giFlags = giFlags;
+    options.stages = stages;
     if (rows) {
       options.useRows = true;
       options.rows = *rows;
@@ -210,6 +211,12 @@ int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t siz
 int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile) {
   if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_render_frame: null renderer");
   LGH_TRY(r->declareAndExecute(mode, denoiserRadius, giFlags, rows, profile != 0))
+}
+
+int lgh_render_stages(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t stages) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_render_stages: null renderer");
+  if (mode != LGH_MODE_FUSED || (stages & ~uint32_t(LGH_STAGE_ALL)) != 0) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_render_stages: fused mode and stage bits 1..8 only");
+  LGH_TRY(r->declareAndExecute(mode, denoiserRadius, giFlags, rows, false, stages))
 }
 
 int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows) {

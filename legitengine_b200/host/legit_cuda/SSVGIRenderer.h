@@ -51,6 +51,9 @@ struct FrameOptions {
   uint32_t giFlags = LGCU_GI_DEFAULT;   // LGCU_GI_STRICT selects the shader-order parity kernel
   bool useRows = false;                 // multi-GPU strip: only rows [rows.y0, rows.y1) of the frame are produced
   lgcu_rows rows{0, 0};
+  // Multi-GPU strips run the fused frame in stages with a halo exchange between them; a single GPU runs all.
+  enum Stage : uint32_t { StageFront = 1, StageChains = 2, StageGather = 4, StageFinal = 8, StageAll = 15 };
+  uint32_t stages = StageAll;
 };
 
 class SSVGIRenderer {
@@ -86,9 +89,11 @@ public:
     const bool useRows = options.useRows;
     auto rowsOf = [useRows](const PassData &pd) -> const lgcu_rows * { return useRows ? &pd.rowsStorage : nullptr; };
 
+    const uint32_t stages = options.mode == FrameOptions::Mode::Fused ? options.stages : uint32_t(FrameOptions::StageAll);
     // rendering shadow map (:61-104) — the light's depth arrives rasterised with the scene
     vk::Extent2D shadowMapExtent(res->shadowMap.baseSize.x, res->shadowMap.baseSize.y);
-    graph->AddPass(RenderGraph::RenderPassDesc()
+    if (stages & FrameOptions::StageFront)
+      graph->AddPass(RenderGraph::RenderPassDesc()
                        .SetDepthAttachment(res->shadowMap.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
                        .SetStorageBuffers({scene->lightDepthProxy->Id()})
                        .SetRenderAreaExtent(shadowMapExtent)
@@ -187,7 +192,8 @@ public:
     } else if (!useRows || (options.rows.y0 % 16 == 0 && (options.rows.y1 % 16 == 0 || options.rows.y1 == viewportExtent.height))) {
       // K1 + K2 + level-0 blur copies + mip levels 1..4 of both chains in one pass over the fragments (lgcu_frame_front), then the
       // remaining blur / mip work of both chains in one launch (lgcu_frame_chains): 2 kernels for 41 reference passes (:106-221)
-      graph->AddPass(RenderGraph::RenderPassDesc()
+      if (stages & FrameOptions::StageFront)
+        graph->AddPass(RenderGraph::RenderPassDesc()
                          .SetColorAttachments({res->albedo.imageViewProxy->Id(), res->emissive.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
                                                res->depthMoments.imageViewProxy->Id(), res->directLight.imageViewProxy->Id(),
                                                res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id()},
@@ -212,7 +218,8 @@ public:
                                                       passContext.GetColorAttachment(6)->GetDesc(), rowsOf(passData), passContext.GetStream()),
                                      "FrameFrontPass");
                          }));
-      graph->AddPass(RenderGraph::RenderPassDesc()
+      if (stages & FrameOptions::StageChains)
+        graph->AddPass(RenderGraph::RenderPassDesc()
                          .SetStorageImages({res->directLight.imageViewProxy->Id(), res->blurredDirectLight.imageViewProxy->Id(), res->depthMoments.imageViewProxy->Id(),
                                             res->blurredDepthMoments.imageViewProxy->Id()})
                          .SetRenderAreaExtent(viewportExtent)
@@ -283,7 +290,7 @@ public:
       pd.memoryPool->EndSet();
       return shaderDataBuffer;
     };
-    if (packedGather) {
+    if (packedGather && (stages & FrameOptions::StageGather)) {
       // builds the gather's private acceleration structure (quad-packed depth pyramid) in a transient buffer
       graph->AddPass(RenderGraph::RenderPassDesc()
                          .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
@@ -304,7 +311,7 @@ public:
                                      "GatherPackPass");
                          }));
     }
-    {
+    if (stages & FrameOptions::StageGather) {
       RenderGraph::RenderPassDesc desc;
       desc.SetColorAttachments({res->indirectLight.imageViewProxy->Id()})
           .SetInputImages({res->blurredDirectLight.imageViewProxy->Id(), res->blurredDepthMoments.imageViewProxy->Id(), res->normal.imageViewProxy->Id(),
@@ -388,7 +395,7 @@ public:
                                                        passContext.GetColorAttachment(0)->GetDesc(), rowsOf(passData), passContext.GetStream()),
                                      "GatheringPass");
                          }));
-    } else {
+    } else if (stages & FrameOptions::StageFinal) {
       // K6 + K7 fused
       graph->AddPass(RenderGraph::RenderPassDesc()
                          .SetColorAttachments({res->denoisedIndirectLight.imageViewProxy->Id(), frameInfo.swapchainImageViewProxyId})
