@@ -47,6 +47,11 @@ def parse_args():
     ap.add_argument("--strict", action="store_true", help="use the shader-order parity gather kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 30))")
+    ap.add_argument("--shard", default="replicas", choices=["replicas", "strips"],
+                    help="N > 1: replicas = independent frames per GPU (weak scaling, BASELINE configs[4]); strips = ONE frame cut into row strips "
+                         "with NVLink halo exchange (strong scaling, BASELINE configs[3])")
+    ap.add_argument("--no-present", action="store_true", help="strips: skip the composite of the swapchain strips on rank 0")
+    ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -304,6 +309,128 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_strips(args, rank: int, world: int, local_rank: int):
+    """ONE frame of the workload cut into row strips over the ranks (legitengine_b200/multigpu.py): per step every rank renders
+    its strip in stages with halo exchanges over NCCL/NVLink in between, then the swapchain strips are composited on rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    from legitengine_b200 import abi, multigpu, scene, sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H = workload_size(args.workload)
+    m = scene.frame_matrices(W, H)
+    seed = 0xC0FFEE
+    bounds = sharding.strip_bounds(H, world)
+    y0, y1 = bounds[rank]
+    # every rank generates (and keeps in pinned memory) only its own strip of the rasterised scene
+    frag_host = torch.empty((max(y1 - y0, 1), W * 32), dtype=torch.uint8).pin_memory()
+    frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
+    full_view_ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
+    scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
+    objects = scene.scene_objects(seed)
+    shadow = torch.from_numpy(scene.scene_shadow_map(seed, m)).pin_memory()
+    swap_host = torch.empty((H, W * 4), dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.Stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        sr = multigpu.StripRenderer(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present)
+        sr.renderer.upload_objects(objects.ctypes.data, len(objects))
+        sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
+        sr.upload_strip(full_view_ptr, W * 32)
+        gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
+
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, steps, warmup, sample_clocks=False):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            sampler = ClockSampler(local_rank) if sample_clocks else None
+            if sampler:
+                sampler.start()
+            ev0.record(stream)
+            for _ in range(steps):
+                fn()
+            ev1.record(stream)
+            barrier()
+            clocks = sampler.stop() if sampler else None
+            t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()), clocks
+
+        warm = max(args.warmup, 3)
+        use_graph = not args.no_graph
+        if use_graph:
+            sr.capture(gi_flags)
+        frame = sr.replay if use_graph else (lambda: sr.render(gi_flags))
+        ms_total, clocks = timed(frame, args.steps, warm, sample_clocks=True)
+        ms_per_step = ms_total / args.steps
+        received = sr.received_bytes
+
+        def e2e_step():
+            sr.upload_strip(full_view_ptr, W * 32)
+            frame()
+            if rank == 0:
+                sr.renderer.download_swapchain(swap_host.data_ptr(), W * 4)
+
+        e2e_steps = args.e2e_steps or min(args.steps, 30)
+        e2e_ms, _ = timed(e2e_step, e2e_steps, 3)
+        recv_all = torch.tensor([received], device="cuda", dtype=torch.int64)
+        dist.all_reduce(recv_all)
+    if rank == 0:
+        npx = W * H
+        peak, peak_src = measured_peak_gbs()
+        frame_bytes = FRAME_BYTES_PER_PX * npx + SHADOW_MAP_BYTES * world
+        line = {
+            "metric": METRIC, "value": npx / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{W}x{H} full GI frame tile-sharded into {world} row strips with NVLink halo exchange (BASELINE configs[3])",
+                "pass_list": "fused stages: front | exchange | chains | exchange | gather + final | composite on rank 0",
+                "strips": bounds, "present": not args.no_present, "cuda_graph": use_graph,
+                "exchange_bytes_per_frame_all_ranks": int(recv_all.item()),
+                "l2": "inputs larger than L2 (per-GPU strip working set > 126 MB at 8K / 8 GPUs)",
+            },
+            "clocks": clocks,
+            "e2e": {"value": npx / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": 5 * args.steps * world,
+            "kernels_per_frame": 5,
+            "roofline_frame": {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                               "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes": frame_bytes,
+                               "note": "whole frame over all GPUs, pass-granular algorithmic bytes; peak = N x measured single-GPU HBM copy bandwidth"},
+        }
+        print(json.dumps(line), flush=True)
+    # tear-down: release the captured graph before the communicator; if NCCL still refuses to shut down cleanly, leave anyway
+    torch.cuda.synchronize()
+    sr.release_graph()
+    dist.barrier()
+    sys.stdout.flush()
+    if use_graph:
+        os._exit(0)  # a process group whose transfers were graph-captured can block in destroy_process_group
+    sr.close()
+    dist.destroy_process_group()
+
+
+class _OffsetRows:
+    """Minimal stand-in for a full-height fragment array whose storage starts at row y0 (only .ctypes.data / .strides are used)."""
+
+    def __init__(self, frags, y0):
+        self._frags, self._y0 = frags, y0
+        self.strides = frags.strides
+
+        class _C:
+            data = frags.ctypes.data - y0 * frags.strides[0]
+
+        self.ctypes = _C()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -311,6 +438,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if world > 1 and args.shard == "strips":
+        run_strips(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

@@ -67,6 +67,7 @@ class StripRenderer:
         self._views: Optional[Dict[str, Tuple[object, abi.LgcuImage]]] = None
         self._torch = torch
         self.received_bytes = 0
+        self._graph = None
 
     def _ensure_views(self):
         if self._views is None:  # image memory exists after the first Execute
@@ -96,6 +97,25 @@ class StripRenderer:
         if self.present:
             got += run_transfers(self.plan_present, views, self.rank, self.dist)
         self.received_bytes = got
+
+    def capture(self, gi_flags: int = abi.GI_DEFAULT) -> None:
+        """Captures one whole sharded frame — the CUDA kernels of every stage AND the NCCL halo transfers between them — into a
+        CUDA graph on the renderer's stream (which must be the current torch stream). At 8 GPUs a strip is well under a
+        millisecond of GPU work, so per-frame launch + Python cost has to disappear for the strips to scale."""
+        torch = self._torch
+        self.render(gi_flags)  # allocations, NCCL connection set-up and the cached views must exist before capture
+        self.render(gi_flags)
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=torch.cuda.current_stream()):
+            self.render(gi_flags)
+
+    def replay(self) -> None:
+        self._graph.replay()
+
+    def release_graph(self) -> None:
+        self._graph = None
 
     def _allocate_idle(self):
         # a rank with an empty strip still has to allocate its images once to take part in the collectives' bookkeeping
