@@ -51,6 +51,8 @@ def parse_args():
                     help="N > 1: replicas = independent frames per GPU (weak scaling, BASELINE configs[4]); strips = ONE frame cut into row strips "
                          "with NVLink halo exchange (strong scaling, BASELINE configs[3])")
     ap.add_argument("--no-present", action="store_true", help="strips: skip the composite of the swapchain strips on rank 0")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="strips: p2p = our copy/flag kernels over NVLink peer memory (CUDA IPC); nccl = torch.distributed send/recv per slab")
     ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -337,7 +339,8 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     stream = torch.cuda.Stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
-        sr = multigpu.StripRenderer(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present)
+        cls = multigpu.P2PStripRenderer if args.transport == "p2p" else multigpu.StripRenderer
+        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present)
         sr.renderer.upload_objects(objects.ctypes.data, len(objects))
         sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
         sr.upload_strip(full_view_ptr, W * 32)
@@ -394,6 +397,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
                 "workload": f"{W}x{H} full GI frame tile-sharded into {world} row strips with NVLink halo exchange (BASELINE configs[3])",
                 "pass_list": "fused stages: front | exchange | chains | exchange | gather + final | composite on rank 0",
                 "strips": bounds, "present": not args.no_present, "cuda_graph": use_graph,
+                "transport": "own copy + flag kernels over NVLink peer memory (CUDA IPC)" if args.transport == "p2p" else "NCCL send/recv per slab",
                 "exchange_bytes_per_frame_all_ranks": int(recv_all.item()),
                 "l2": "inputs larger than L2 (per-GPU strip working set > 126 MB at 8K / 8 GPUs)",
             },
@@ -412,7 +416,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     sr.release_graph()
     dist.barrier()
     sys.stdout.flush()
-    if use_graph:
+    if use_graph and args.transport == "nccl":
         os._exit(0)  # a process group whose transfers were graph-captured can block in destroy_process_group
     sr.close()
     dist.destroy_process_group()

@@ -228,6 +228,19 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
                               const lgcu_image *blurredDirectLight, const lgcu_image *albedo,
                               const lgcu_image *swapchain, const lgcu_rows *rows, void *stream);
 
+/* ---- peer-to-peer row exchange for the strip-sharded frame (no counterpart in the single-GPU reference) -------
+ * All pointers are DEVICE addresses valid in the calling process; a peer GPU's memory is addressed through a CUDA-IPC mapping, and
+ * loads / stores on it travel over NVLink. Everything is enqueue-only and CUDA-graph capturable. */
+typedef struct lgcu_row_copy { const void *src; void *dst; uint64_t bytes; } lgcu_row_copy; /* 16-byte aligned, multiple of 16 */
+/* Copies `count` contiguous slabs in one kernel launch per 64 slabs (rows of an image level are contiguous, so a halo is a slab). */
+int lgcu_copy_rows(const lgcu_row_copy *copies, uint32_t count, void *stream);
+/* *frameCounter += 1 on the stream (device memory; keeps signal / wait values correct under graph replay). */
+int lgcu_frame_counter_bump(uint32_t *frameCounter, void *stream);
+/* *flags[i] = *frameCounter for i < count (<= 32), after a system-scope fence: "my work enqueued before this call is done". */
+int lgcu_signal_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, void *stream);
+/* Blocks the stream (a one-warp spinning kernel) until *flags[i] >= *frameCounter - lag for every i < count. */
+int lgcu_wait_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, uint32_t lag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

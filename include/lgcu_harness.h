@@ -48,6 +48,15 @@ int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uin
 enum { LGH_STAGE_FRONT = 1, LGH_STAGE_CHAINS = 2, LGH_STAGE_GATHER = 4, LGH_STAGE_FINAL = 8, LGH_STAGE_ALL = 15 };
 int lgh_render_stages(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t stages);
 
+/* CUDA-IPC plumbing of the peer-to-peer strip exchange (one process per GPU): export an image's allocation (valid after the first
+ * frame), open / close a peer's handle in this process, and small zero-initialised device allocations for the flag words. */
+int lgh_ipc_export_image(lgh_renderer *r, const char *name, unsigned char handle[64], uint64_t *bytes);
+int lgh_ipc_export_ptr(void *devicePtr, unsigned char handle[64]);
+int lgh_ipc_open(const unsigned char handle[64], void **devicePtr);
+int lgh_ipc_close(void *devicePtr);
+int lgh_device_alloc_zeroed(uint64_t bytes, void **devicePtr);
+int lgh_device_free(void *devicePtr);
+
 /* Capture the same frame into a CUDA graph once (after at least one lgh_render_frame with the same arguments has
  * allocated the images), then replay it with a single launch per frame. */
 int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows);

@@ -30,6 +30,7 @@ CUDA_UNITS = {
     "k_front.cu": ["-fmad=false"],
     "k_gather_strict.cu": ["-fmad=false"],
     "k_gather_fast.cu": [],
+    "k_p2p.cu": [],
     "lgcu_api.cu": ["-fmad=false"],
 }
 

@@ -84,6 +84,10 @@ DenoiserData = _packed("DenoiserData", [("viewMatrix", LgcuMat4), ("projMatrix",
 FinalGathererData = _packed("FinalGathererData", [("viewMatrix", LgcuMat4), ("projMatrix", LgcuMat4)])
 
 
+class RowCopy(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_uint64)]
+
+
 class ClearValues(C.Structure):
     _fields_ = [("color", C.c_float * 4), ("depth", C.c_float)]
 
@@ -166,6 +170,12 @@ def load_lgcu() -> C.CDLL:
         lib.lgcu_format_texel_size.restype = C.c_uint32
         lib.lgcu_image_layout.argtypes = [IMG, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.lgcu_image_layout.restype = C.c_uint64
+        lib.lgcu_copy_rows.argtypes = [P(RowCopy), C.c_uint32, C.c_void_p]
+        lib.lgcu_frame_counter_bump.argtypes = [C.c_void_p, C.c_void_p]
+        lib.lgcu_signal_flags.argtypes = [P(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.lgcu_wait_flags.argtypes = [P(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        for fn in (lib.lgcu_copy_rows, lib.lgcu_frame_counter_bump, lib.lgcu_signal_flags, lib.lgcu_wait_flags):
+            fn.restype = C.c_int
         lib.lgcu_gather_scratch_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         lib.lgcu_gather_scratch_bytes.restype = C.c_uint64
         _lgcu = lib

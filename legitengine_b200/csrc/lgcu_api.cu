@@ -460,6 +460,58 @@ int lgcu_frame_chains(const lgcu_image *directLight, const lgcu_image *blurredDi
   return cudaStatus(launchFrameChains(a, static_cast<cudaStream_t>(stream)), "frame_chains");
 }
 
+// ------------------------------------------------------------------------------------------------------- peer-to-peer rows
+int lgcu_copy_rows(const lgcu_row_copy *copies, uint32_t count, void *stream) {
+  if (!copies && count) return fail(LGCU_ERR_INVALID_ARGUMENT, "copy_rows: null list");
+  const int sms = smCountOfCurrentDevice();
+  for (uint32_t begin = 0; begin < count; begin += kMaxCopies) {
+    RowCopyArgs a;
+    a.count = 0;
+    uint64_t units = 0;
+    for (uint32_t i = begin; i < count && a.count < kMaxCopies; i++) {
+      const lgcu_row_copy &c = copies[i];
+      if (!c.bytes) continue;
+      if (!c.src || !c.dst || (c.bytes % 16) != 0 || (reinterpret_cast<uintptr_t>(c.src) % 16) != 0 || (reinterpret_cast<uintptr_t>(c.dst) % 16) != 0)
+        return fail(LGCU_ERR_INVALID_ARGUMENT, "copy_rows: slab %u must be non-null, 16-byte aligned and a multiple of 16 bytes", i);
+      units += c.bytes / 16;
+      a.src[a.count] = c.src;
+      a.dst[a.count] = c.dst;
+      a.unitEnd[a.count] = units;
+      a.count++;
+    }
+    const int st = cudaStatus(launchRowCopies(a, sms, static_cast<cudaStream_t>(stream)), "copy_rows");
+    if (st != LGCU_OK) return st;
+  }
+  return LGCU_OK;
+}
+
+static bool fillFlags(uint32_t *const *flags, uint32_t count, FlagArgs *a) {
+  if (count > (uint32_t)kMaxFlags || (!flags && count)) return false;
+  a->count = (int)count;
+  for (uint32_t i = 0; i < count; i++) {
+    if (!flags[i]) return false;
+    a->flags[i] = flags[i];
+  }
+  return true;
+}
+
+int lgcu_frame_counter_bump(uint32_t *frameCounter, void *stream) {
+  if (!frameCounter) return fail(LGCU_ERR_INVALID_ARGUMENT, "frame_counter_bump: null counter");
+  return cudaStatus(launchBumpFrame(frameCounter, static_cast<cudaStream_t>(stream)), "frame_counter_bump");
+}
+
+int lgcu_signal_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, void *stream) {
+  FlagArgs a;
+  if (!frameCounter || !fillFlags(flags, count, &a)) return fail(LGCU_ERR_INVALID_ARGUMENT, "signal_flags: bad flag list (max %d)", kMaxFlags);
+  return cudaStatus(launchSignal(a, frameCounter, static_cast<cudaStream_t>(stream)), "signal_flags");
+}
+
+int lgcu_wait_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, uint32_t lag, void *stream) {
+  FlagArgs a;
+  if (!frameCounter || !fillFlags(flags, count, &a)) return fail(LGCU_ERR_INVALID_ARGUMENT, "wait_flags: bad flag list (max %d)", kMaxFlags);
+  return cudaStatus(launchWait(a, frameCounter, (int)lag, static_cast<cudaStream_t>(stream)), "wait_flags");
+}
+
 // ------------------------------------------------------------------------------------------------------- K5
 static bool fillGatherArgs(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight, const lgcu_image *blurredDepthMoments,
                            const lgcu_image *normal, const lgcu_image *depthStencil, const lgcu_image *indirectLight, const lgcu_rows *rows, GatherArgs *a,

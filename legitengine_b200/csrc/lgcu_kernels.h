@@ -122,6 +122,22 @@ struct ChainsArgs { // everything of K3 + K4 that the front kernel leaves: blur 
   RowRange rows;  // base rows
 };
 
+constexpr int kMaxCopies = 64, kMaxFlags = 32;
+struct RowCopyArgs { // contiguous slabs (16-byte multiples), any of them possibly in a peer GPU's memory
+  const void *src[kMaxCopies];
+  void *dst[kMaxCopies];
+  uint64_t unitEnd[kMaxCopies]; // running end of each slab in 16-byte units
+  int count;
+};
+struct FlagArgs {
+  uint32_t *flags[kMaxFlags];
+  int count;
+};
+cudaError_t launchRowCopies(const RowCopyArgs &a, int smCount, cudaStream_t s);
+cudaError_t launchBumpFrame(uint32_t *frame, cudaStream_t s);
+cudaError_t launchSignal(const FlagArgs &a, const uint32_t *frame, cudaStream_t s);
+cudaError_t launchWait(const FlagArgs &a, const uint32_t *frame, int lag, cudaStream_t s);
+
 cudaError_t launchFrameFront(const FrontArgs &a, int smCount, cudaStream_t s);
 cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s);
 cudaError_t launchGBufferResolve(const GBufferArgs &a, cudaStream_t s);

@@ -42,6 +42,13 @@ def load_harness() -> C.CDLL:
         lib.lgh_upload_light_depth.argtypes = [R, C.c_void_p, C.c_uint32]
         lib.lgh_render_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         lib.lgh_render_stages.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
+        H64 = C.c_ubyte * 64
+        lib.lgh_ipc_export_image.argtypes = [R, C.c_char_p, H64, C.POINTER(C.c_uint64)]
+        lib.lgh_ipc_export_ptr.argtypes = [C.c_void_p, H64]
+        lib.lgh_ipc_open.argtypes = [H64, C.POINTER(C.c_void_p)]
+        lib.lgh_ipc_close.argtypes = [C.c_void_p]
+        lib.lgh_device_alloc_zeroed.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        lib.lgh_device_free.argtypes = [C.c_void_p]
         lib.lgh_capture_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS]
         lib.lgh_replay_frame.argtypes = [R]
         lib.lgh_captured_kernel_count.argtypes = [R]
@@ -163,3 +170,36 @@ class Renderer:
             _check(self.lib.lgh_download_image(self.handle, name.encode(), l, C.c_void_p(ptr), host.desc.levelPitch[l], 0, h), "lgh_download_image")
         self.sync()
         return host
+
+
+# ---- CUDA IPC helpers (peer-to-peer strip exchange) -----------------------------------------------------------------------
+def ipc_export_image(renderer: "Renderer", name: str) -> bytes:
+    h = (C.c_ubyte * 64)()
+    _check(renderer.lib.lgh_ipc_export_image(renderer.handle, name.encode(), h, None), "lgh_ipc_export_image")
+    return bytes(h)
+
+
+def ipc_export_ptr(ptr: int) -> bytes:
+    h = (C.c_ubyte * 64)()
+    _check(load_harness().lgh_ipc_export_ptr(C.c_void_p(ptr), h), "lgh_ipc_export_ptr")
+    return bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    out = C.c_void_p()
+    _check(load_harness().lgh_ipc_open((C.c_ubyte * 64).from_buffer_copy(handle), C.byref(out)), "lgh_ipc_open")
+    return int(out.value)
+
+
+def ipc_close(ptr: int) -> None:
+    load_harness().lgh_ipc_close(C.c_void_p(ptr))
+
+
+def device_alloc_zeroed(nbytes: int) -> int:
+    out = C.c_void_p()
+    _check(load_harness().lgh_device_alloc_zeroed(nbytes, C.byref(out)), "lgh_device_alloc_zeroed")
+    return int(out.value)
+
+
+def device_free(ptr: int) -> None:
+    load_harness().lgh_device_free(C.c_void_p(ptr))

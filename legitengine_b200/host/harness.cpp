@@ -219,6 +219,49 @@ int lgh_render_stages(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, ui
   LGH_TRY(r->declareAndExecute(mode, denoiserRadius, giFlags, rows, false, stages))
 }
 
+// ---- CUDA IPC plumbing for the peer-to-peer strip exchange (one process per GPU) -------------------------------------------
+int lgh_ipc_export_image(lgh_renderer *r, const char *name, unsigned char handle[64], uint64_t *bytes) {
+  if (!r || !name || !handle) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_ipc_export_image: null argument");
+  ImageView *view = r->findImage(name);
+  if (!view) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_ipc_export_image: unknown or unresolved image '%s'", name);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, view->GetImageData()->GetDesc().base);
+  if (e != cudaSuccess) return setError(LGCU_ERR_CUDA, "cudaIpcGetMemHandle(%s): %s", name, cudaGetErrorString(e));
+  std::memcpy(handle, &h, 64);
+  if (bytes) *bytes = view->GetImageData()->GetByteSize();
+  return LGCU_OK;
+}
+int lgh_ipc_export_ptr(void *devicePtr, unsigned char handle[64]) {
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, devicePtr);
+  if (e != cudaSuccess) return setError(LGCU_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  std::memcpy(handle, &h, 64);
+  return LGCU_OK;
+}
+int lgh_ipc_open(const unsigned char handle[64], void **devicePtr) {
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  const cudaError_t e = cudaIpcOpenMemHandle(devicePtr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return setError(LGCU_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+  return LGCU_OK;
+}
+int lgh_ipc_close(void *devicePtr) {
+  const cudaError_t e = cudaIpcCloseMemHandle(devicePtr);
+  if (e != cudaSuccess) return setError(LGCU_ERR_CUDA, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
+  return LGCU_OK;
+}
+int lgh_device_alloc_zeroed(uint64_t bytes, void **devicePtr) {
+  cudaError_t e = cudaMalloc(devicePtr, bytes ? bytes : 1);
+  if (e == cudaSuccess) e = cudaMemset(*devicePtr, 0, bytes);
+  if (e != cudaSuccess) return setError(LGCU_ERR_CUDA, "lgh_device_alloc_zeroed: %s", cudaGetErrorString(e));
+  return LGCU_OK;
+}
+int lgh_device_free(void *devicePtr) {
+  cudaFree(devicePtr);
+  return LGCU_OK;
+}
+
 int lgh_capture_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows) {
   if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_capture_frame: null renderer");
   try {

@@ -125,3 +125,153 @@ class StripRenderer:
     def close(self):
         self._views = None
         self.renderer.close()
+
+
+class P2PStripRenderer(StripRenderer):
+    """Strip renderer whose halo rows move through our own kernels over NVLink peer memory (CUDA IPC mappings) instead of NCCL:
+    per exchange ONE copy kernel pulls every slab this rank needs straight out of the owners' images (lgcu_copy_rows), ordered
+    by flag words that the owners' streams write into this GPU's memory (lgcu_signal_flags / lgcu_wait_flags). The swapchain
+    strips are PUSHED into the presenting rank's image as soon as a rank finishes. torch.distributed is used once, to swap the
+    IPC handles. Per frame and rank (F = frame number, bumped on the device so the whole frame replays from a CUDA graph):
+
+        bump F | root: signal FREE=F to pushers | wait ACK >= F-1 from my pullers
+        front  | signal FRONT=F to chain pullers  | wait FRONT >= F from chain sources  | pull chain halos
+        chains | signal CHAINS=F to gather pullers | wait CHAINS >= F from gather sources | pull gather halos | signal ACK=F to my sources
+        gather + final | pushers: wait FREE >= F, push strip into root's swapchain, signal DELIVERED=F | root: wait DELIVERED >= F
+
+    No wait depends on a later signal of the waiting GPU, streams are in order, so the protocol cannot deadlock."""
+
+    FRONT, CHAINS, DELIVERED, ACK, FREE = range(5)
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._lgcu = abi.load_lgcu()
+        if not kwargs.get("stream"):
+            raise ValueError("P2PStripRenderer needs an explicit CUDA stream (the same one the harness renders on)")
+        self._stream = C.c_void_p(kwargs["stream"])
+        self._ready = False
+        self._peer_ptrs: List[int] = []
+
+    # -- one-time set-up ----------------------------------------------------------------------------------------------------
+    def _setup(self):
+        torch, dist, rank, world = self._torch, self.dist, self.rank, self.world
+        # image memory exists after a first Execute of every stage
+        self.renderer.render_stages(harness.STAGE_ALL, self.rows if self.rows[1] > self.rows[0] else (0, 0))
+        self.renderer.sync()
+        self._flags = harness.device_alloc_zeroed(4096)
+        mine = {name: harness.ipc_export_image(self.renderer, name) for name in self.EXCHANGED}
+        mine["__flags__"] = harness.ipc_export_ptr(self._flags)
+        everyone: List[Optional[dict]] = [None] * world
+        dist.all_gather_object(everyone, mine)
+        base: List[Dict[str, int]] = []
+        for peer in range(world):
+            if peer == rank:
+                base.append({name: int(self.renderer.image_desc(name).base) for name in self.EXCHANGED} | {"__flags__": self._flags})
+            else:
+                opened = {name: harness.ipc_open(h) for name, h in everyone[peer].items()}
+                self._peer_ptrs += list(opened.values())
+                base.append(opened)
+        desc = {name: self.renderer.image_desc(name) for name in self.EXCHANGED}
+
+        def slab(t: sharding.Transfer):
+            d = desc[t.image]
+            pitch = int(d.levelPitch[t.level])
+            return int(d.levelOffset[t.level]) + t.row0 * pitch, (t.row1 - t.row0) * pitch
+
+        def copies(plan, pull: bool):
+            items = []
+            for t in plan:
+                if (t.dst if pull else t.src) != rank:
+                    continue
+                off, nbytes = slab(t)
+                items.append(abi.RowCopy(base[t.src][t.image] + off, base[t.dst][t.image] + off, nbytes))
+            return (abi.RowCopy * max(len(items), 1))(*items), len(items)
+
+        def flag_list(stage: int, owners, writer: int):
+            """addresses of flag word (stage, writer) in the memory of each rank in `owners`"""
+            ptrs = [base[o]["__flags__"] + 4 * (stage * world + writer) for o in sorted(owners)]
+            return (C.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
+
+        def local_flags(stage: int, writers):
+            ptrs = [self._flags + 4 * (stage * world + w) for w in sorted(writers)]
+            return (C.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
+
+        pc, pg = self.plan_chains, self.plan_gather
+        pp = self.plan_present if self.present else []
+        self._counter = C.c_void_p(self._flags + 4 * (5 * world))
+        self._pull_chains, self._pull_gather, self._push = copies(pc, True), copies(pg, True), copies(pp, False)
+        chain_pullers, chain_sources = {t.dst for t in pc if t.src == rank}, {t.src for t in pc if t.dst == rank}
+        gather_pullers, gather_sources = {t.dst for t in pg if t.src == rank}, {t.src for t in pg if t.dst == rank}
+        pushers = {t.src for t in pp}
+        self._sig_front, self._wait_front = flag_list(self.FRONT, chain_pullers, rank), local_flags(self.FRONT, chain_sources)
+        self._sig_chains, self._wait_chains = flag_list(self.CHAINS, gather_pullers, rank), local_flags(self.CHAINS, gather_sources)
+        self._sig_ack, self._wait_ack = flag_list(self.ACK, chain_sources | gather_sources, rank), local_flags(self.ACK, chain_pullers | gather_pullers)
+        self._is_pusher = rank in pushers
+        self._sig_free = flag_list(self.FREE, pushers, rank) if rank == self.root else ((C.c_void_p * 1)(), 0)
+        self._wait_free = local_flags(self.FREE, {self.root}) if self._is_pusher else ((C.c_void_p * 1)(), 0)
+        self._sig_delivered = flag_list(self.DELIVERED, {self.root}, rank) if self._is_pusher else ((C.c_void_p * 1)(), 0)
+        self._wait_delivered = local_flags(self.DELIVERED, pushers) if rank == self.root else ((C.c_void_p * 1)(), 0)
+        self.received_bytes = sum(c.bytes for c in self._pull_chains[0][: self._pull_chains[1]]) + sum(c.bytes for c in self._pull_gather[0][: self._pull_gather[1]])
+        torch.cuda.synchronize()
+        dist.barrier()
+        self._ready = True
+
+    # -- per-frame ------------------------------------------------------------------------------------------------------------
+    def _signal(self, lst):
+        if lst[1]:
+            abi.check(self._lgcu.lgcu_signal_flags(lst[0], lst[1], self._counter, self._stream), "lgcu_signal_flags")
+
+    def _wait(self, lst, lag=0):
+        if lst[1]:
+            abi.check(self._lgcu.lgcu_wait_flags(lst[0], lst[1], self._counter, lag, self._stream), "lgcu_wait_flags")
+
+    def _copy(self, lst):
+        if lst[1]:
+            abi.check(self._lgcu.lgcu_copy_rows(lst[0], lst[1], self._stream), "lgcu_copy_rows")
+
+    def render(self, gi_flags: int = abi.GI_DEFAULT) -> None:
+        if not self._ready:
+            self._setup()
+        r, rows = self.renderer, self.rows
+        have = rows[1] > rows[0]
+        abi.check(self._lgcu.lgcu_frame_counter_bump(self._counter, self._stream), "lgcu_frame_counter_bump")
+        self._signal(self._sig_free)
+        self._wait(self._wait_ack, lag=1)
+        if have:
+            r.render_stages(harness.STAGE_FRONT, rows, gi_flags=gi_flags)
+        self._signal(self._sig_front)
+        self._wait(self._wait_front)
+        self._copy(self._pull_chains)
+        if have:
+            r.render_stages(harness.STAGE_CHAINS, rows, gi_flags=gi_flags)
+        self._signal(self._sig_chains)
+        self._wait(self._wait_chains)
+        self._copy(self._pull_gather)
+        self._signal(self._sig_ack)
+        if have:
+            r.render_stages(harness.STAGE_GATHER | harness.STAGE_FINAL, rows, gi_flags=gi_flags)
+        if self._is_pusher:
+            self._wait(self._wait_free)
+            self._copy(self._push)
+            self._signal(self._sig_delivered)
+        self._wait(self._wait_delivered)
+
+    def capture(self, gi_flags: int = abi.GI_DEFAULT) -> None:
+        torch = self._torch
+        self.render(gi_flags)
+        self.render(gi_flags)
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=torch.cuda.current_stream()):
+            self.render(gi_flags)
+
+    def close(self):
+        self._torch.cuda.synchronize()
+        self.dist.barrier()  # nobody may still be reading this rank's memory
+        for p in self._peer_ptrs:
+            harness.ipc_close(p)
+        self._peer_ptrs = []
+        if self._ready:
+            harness.device_free(self._flags)
+        super().close()

@@ -18,6 +18,7 @@ def main():
     from legitengine_b200 import abi, harness, multigpu, scene
 
     W, H = int(sys.argv[1]), int(sys.argv[2])
+    transport = sys.argv[3] if len(sys.argv) > 3 else "nccl"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -28,13 +29,18 @@ def main():
         whole.upload_scene(sc)
         whole.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
         whole.sync()
-        sr = multigpu.StripRenderer(W, H, rank, world, dist, stream=stream.cuda_stream)
+        cls = multigpu.P2PStripRenderer if transport == "p2p" else multigpu.StripRenderer
+        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream)
         # only this rank's strip of the fragments is uploaded: the rest of the fragment buffer stays unwritten
         sr.renderer.upload_objects(sc.objects.ctypes.data, len(sc.objects))
         sr.renderer.upload_light_depth(np.ascontiguousarray(sc.shadow_map).ctypes.data, sc.shadow_map.shape[0])
         sr.upload_strip(sc.fragments.ctypes.data, sc.fragments.strides[0])
-        for _ in range(2):  # twice: the second frame runs on warm allocations / cached views
+        for _ in range(3):  # several frames: warm allocations / cached views, and the frame-to-frame ack protocol of the p2p transport
             sr.render()
+        if transport == "p2p":  # and once more from a CUDA graph (stages + flag kernels + peer copies)
+            sr.capture()
+            sr.replay()
+            sr.replay()
         torch.cuda.synchronize()
         y0, y1 = sr.rows
         errors = []
