@@ -228,6 +228,47 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
                               const lgcu_image *blurredDirectLight, const lgcu_image *albedo,
                               const lgcu_image *swapchain, const lgcu_rows *rows, void *stream);
 
+/* ---- rasterisation front end: "ShadowPass" and the raster half of "GBufferPass"  --------------------
+ * The reference draws every scene object with drawIndexed through the fixed-function rasteriser (SSVGIRenderer.h:63-104 shadow
+ * map, :107-158 G-buffer; vertex stages SH/Common/shadowmapBuilder.vert:32-40 and SH/Common/gBufferBuilder.vert:32-40; pipeline
+ * state LV/Pipeline.h:6-12, 148-178: fill, no culling, depth test LESS + write, depth clamp off, one sample per pixel; viewport =
+ * render area, depth range [0,1], LV/RenderPassCache.h:94-101). These entry points do the same on the CUDA device and hand the
+ * result to the fragment stage: the shadow map image, and the lgcu_fragment buffer lgcu_gbuffer_resolve / lgcu_frame_front consume.
+ * The rasterisation rule (pixel-centre sampling, top-left fill rule, perspective-correct interpolation, near/far clipping per
+ * fragment, first-drawn-wins on equal depth) is stated in DESIGN.md §8. */
+#pragma pack(push, 1)
+/* src/Scene/Mesh.h:209-216 (MeshData::Vertex, 32 bytes; vertex declaration :263-271) */
+typedef struct lgcu_vertex { float pos[3]; float normal[3]; float uv[2]; } lgcu_vertex;
+/* SSVGIRenderer.h:439-447 (ShadowmapBuilderShader::DataBuffer), SH/Common/shadowmapBuilder.vert:8-12 */
+typedef struct lgcu_shadowmap_builder_data { lgcu_mat4 lightViewMatrix, lightProjMatrix; } lgcu_shadowmap_builder_data;
+#pragma pack(pop)
+/* One drawIndexed(indexCount, 1, firstIndex, vertexOffset, 0) with DrawCallData = objects[objectId] bound
+ * (Scene::IterateObjects callback, SSVGIRenderer.h:84-102, 138-156). firstTriangle = number of triangles drawn before this call
+ * in the frame (draw order decides equal-depth fragments); lgcu_raster_prepare_draws fills it. */
+typedef struct lgcu_draw { uint32_t firstIndex, indexCount, vertexOffset, objectId, firstTriangle, reserved[3]; } lgcu_draw;
+/* The scene as the reference's Scene holds it: vertex / index buffers, the per-object constants and the draw list. All four arrays
+ * are DEVICE memory; they are read by the kernels, never by the host. */
+typedef struct lgcu_mesh_scene {
+  const lgcu_vertex *vertices;
+  const uint32_t *indices;
+  const lgcu_draw *draws;
+  const lgcu_draw_call_data *objects;
+  uint32_t nVertices, nIndices, nDraws, nObjects;
+  uint32_t nTriangles; /* sum of indexCount / 3 over the draws (= what lgcu_raster_prepare_draws returned) */
+} lgcu_mesh_scene;
+/* HOST helper: fills draws[i].firstTriangle (draws in HOST memory, before upload) and returns the total triangle count. */
+uint32_t lgcu_raster_prepare_draws(lgcu_draw *hostDraws, uint32_t nDraws);
+/* Bytes of DEVICE scratch (256-byte aligned) the raster calls need for a scene of nTriangles on a width x height target. */
+uint64_t lgcu_raster_scratch_bytes(uint32_t nTriangles, uint32_t width, uint32_t height);
+/* K0 "ShadowPass": depth-only rasterisation from the light into shadowMap (D32F, cleared to 1). */
+int lgcu_raster_shadow_map(const lgcu_shadowmap_builder_data *params, const lgcu_mesh_scene *scene, void *scratch,
+                           uint64_t scratchBytes, const lgcu_image *shadowMap, void *stream);
+/* Raster half of K1 "GBufferPass": visibility + interpolated vertWorldPos / vertWorldNormal per pixel, written as the
+ * lgcu_fragment buffer (width x height, fragmentPitchBytes per row, DEVICE memory) that the fragment-stage entries read. */
+int lgcu_raster_gbuffer(const lgcu_gbuffer_builder_data *params, const lgcu_mesh_scene *scene, void *scratch,
+                        uint64_t scratchBytes, uint32_t width, uint32_t height, lgcu_fragment *fragments,
+                        uint64_t fragmentPitchBytes, const lgcu_rows *rows, void *stream);
+
 /* ---- peer-to-peer row exchange for the strip-sharded frame (no counterpart in the single-GPU reference) -------
  * All pointers are DEVICE addresses valid in the calling process; a peer GPU's memory is addressed through a CUDA-IPC mapping, and
  * loads / stores on it travel over NVLink. Everything is enqueue-only and CUDA-graph capturable. */

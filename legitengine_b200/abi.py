@@ -102,7 +102,16 @@ FRAGMENT_DTYPE = np.dtype(
     [("worldPos", "<f4", 3), ("worldNormal", "<f4", 3), ("objectId", "<u4"), ("ndcDepth", "<f4")]
 )
 DRAW_CALL_DTYPE = np.dtype([("modelMatrix", "<f4", 16), ("albedoColor", "<f4", 4), ("emissiveColor", "<f4", 4)])
-assert FRAGMENT_DTYPE.itemsize == 32 and DRAW_CALL_DTYPE.itemsize == 96
+# rasterisation front end (include/lgcu.h: lgcu_vertex, lgcu_draw, lgcu_mesh_scene, lgcu_shadowmap_builder_data)
+VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("normal", "<f4", 3), ("uv", "<f4", 2)])
+DRAW_DTYPE = np.dtype([("firstIndex", "<u4"), ("indexCount", "<u4"), ("vertexOffset", "<u4"), ("objectId", "<u4"), ("firstTriangle", "<u4"), ("reserved", "<u4", 3)])
+assert FRAGMENT_DTYPE.itemsize == 32 and DRAW_CALL_DTYPE.itemsize == 96 and VERTEX_DTYPE.itemsize == 32 and DRAW_DTYPE.itemsize == 32
+ShadowmapBuilderData = _packed("ShadowmapBuilderData", [("lightViewMatrix", LgcuMat4), ("lightProjMatrix", LgcuMat4)])
+
+
+class MeshScene(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("draws", C.c_void_p), ("objects", C.c_void_p),
+                ("nVertices", C.c_uint32), ("nIndices", C.c_uint32), ("nDraws", C.c_uint32), ("nObjects", C.c_uint32), ("nTriangles", C.c_uint32)]
 
 
 def mat4(values) -> LgcuMat4:
@@ -116,6 +125,12 @@ def mat4(values) -> LgcuMat4:
 P = C.POINTER
 IMG = P(LgcuImage)
 ROWS = P(LgcuRows)
+
+# rasterisation front end: (argtypes without the trailing stream); the oracle variants take host arrays and different targets
+RASTER_SIGNATURES = {
+    "raster_shadow_map": [P(ShadowmapBuilderData), P(MeshScene), C.c_void_p, C.c_uint64, IMG],
+    "raster_gbuffer": [P(GBufferBuilderData), P(MeshScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, ROWS],
+}
 
 # name -> (argtypes without the trailing stream) ; shared by the CUDA library (with stream) and both oracles (without)
 PASS_SIGNATURES = {
@@ -160,7 +175,7 @@ def load_lgcu() -> C.CDLL:
     global _lgcu
     if _lgcu is None:
         lib = _load(lgcu_path(), "CUDA pass library (liblgcu.so)", "run `python -c 'import __graft_entry__ as g; g.build()'`")
-        for name, sig in {**PASS_SIGNATURES, **FUSED_SIGNATURES}.items():
+        for name, sig in {**PASS_SIGNATURES, **FUSED_SIGNATURES, **RASTER_SIGNATURES}.items():
             fn = getattr(lib, "lgcu_" + name)
             fn.argtypes = sig + [C.c_void_p]
             fn.restype = C.c_int
@@ -178,6 +193,10 @@ def load_lgcu() -> C.CDLL:
             fn.restype = C.c_int
         lib.lgcu_gather_scratch_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         lib.lgcu_gather_scratch_bytes.restype = C.c_uint64
+        lib.lgcu_raster_scratch_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.lgcu_raster_scratch_bytes.restype = C.c_uint64
+        lib.lgcu_raster_prepare_draws.argtypes = [C.c_void_p, C.c_uint32]
+        lib.lgcu_raster_prepare_draws.restype = C.c_uint32
         _lgcu = lib
     return _lgcu
 
@@ -199,6 +218,10 @@ def load_scene_lib() -> C.CDLL:
         lib.lgs_frame_matrices.restype = None
         lib.lgs_mat4_inverse.argtypes = [f4, f4]
         lib.lgs_mat4_mul.argtypes = [f4, f4, f4]
+        u32p = P(C.c_uint32)
+        lib.lgs_scene_mesh_counts.argtypes = [C.c_uint32, u32p, u32p, u32p]
+        lib.lgs_scene_mesh_counts.restype = None
+        lib.lgs_scene_mesh.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         _scene = lib
     return _scene
 

@@ -460,6 +460,74 @@ int lgcu_frame_chains(const lgcu_image *directLight, const lgcu_image *blurredDi
   return cudaStatus(launchFrameChains(a, static_cast<cudaStream_t>(stream)), "frame_chains");
 }
 
+// ------------------------------------------------------------------------------------------------------- rasterisation front end
+uint32_t lgcu_raster_prepare_draws(lgcu_draw *hostDraws, uint32_t nDraws) {
+  uint32_t tri = 0;
+  for (uint32_t i = 0; hostDraws && i < nDraws; i++) {
+    hostDraws[i].firstTriangle = tri;
+    tri += hostDraws[i].indexCount / 3;
+  }
+  return tri;
+}
+
+uint64_t lgcu_raster_scratch_bytes(uint32_t nTriangles, uint32_t width, uint32_t height) { return rasterScratchBytes(nTriangles, width, height); }
+
+static bool fillRasterArgs(const lgcu_mesh_scene *scene, const lgcu_mat4 &view, const lgcu_mat4 &proj, void *scratch, uint64_t scratchBytes, uint32_t width,
+                           uint32_t height, RasterArgs *a, int *st) {
+  if (!scene || !scratch) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "raster: null scene / scratch");
+    return false;
+  }
+  if (scene->nTriangles && (!scene->vertices || !scene->indices || !scene->draws || !scene->objects || !scene->nDraws)) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "raster: scene with %u triangles but a null vertex / index / draw / object array", scene->nTriangles);
+    return false;
+  }
+  if ((reinterpret_cast<uintptr_t>(scene->vertices) % 16) != 0 || (reinterpret_cast<uintptr_t>(scratch) % 256) != 0) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "raster: vertices must be 16-byte aligned and scratch 256-byte aligned");
+    return false;
+  }
+  if (width == 0 || height == 0 || width > 32768 || height > 32768 || scratchBytes < rasterScratchBytes(scene->nTriangles, width, height)) {
+    *st = fail(LGCU_ERR_INVALID_ARGUMENT, "raster: %ux%u target needs %llu scratch bytes, got %llu", width, height,
+               (unsigned long long)rasterScratchBytes(scene->nTriangles, width, height), (unsigned long long)scratchBytes);
+    return false;
+  }
+  a->scene = *scene;
+  const lgcu_mat4 vp = lgcu_mat4_mul(&proj, &view); // gl_Position = projMatrix * viewMatrix * v is (proj * view) * v   gBufferBuilder.vert:36
+  a->viewProj = toMat4(vp);
+  a->width = (int)width;
+  a->height = (int)height;
+  a->scratch = scratch;
+  a->fragments = nullptr;
+  a->fragmentPitch = 0;
+  return true;
+}
+
+int lgcu_raster_shadow_map(const lgcu_shadowmap_builder_data *params, const lgcu_mesh_scene *scene, void *scratch, uint64_t scratchBytes,
+                           const lgcu_image *shadowMap, void *stream) {
+  int st = LGCU_OK;
+  RasterArgs a;
+  if (!params) return fail(LGCU_ERR_INVALID_ARGUMENT, "raster_shadow_map: null params");
+  if (!expectFormat(shadowMap, LGCU_FORMAT_D32_SFLOAT, "shadowMap", &st) || !resolveLevel(shadowMap, 0, "shadowMap", &a.depth, &st)) return st;
+  if (!fillRasterArgs(scene, params->lightViewMatrix, params->lightProjMatrix, scratch, scratchBytes, (uint32_t)a.depth.w, (uint32_t)a.depth.h, &a, &st)) return st;
+  a.rows = RowRange{0, a.height};
+  return cudaStatus(launchRaster(a, smCountOfCurrentDevice(), static_cast<cudaStream_t>(stream)), "raster_shadow_map");
+}
+
+int lgcu_raster_gbuffer(const lgcu_gbuffer_builder_data *params, const lgcu_mesh_scene *scene, void *scratch, uint64_t scratchBytes, uint32_t width,
+                        uint32_t height, lgcu_fragment *fragments, uint64_t fragmentPitchBytes, const lgcu_rows *rows, void *stream) {
+  int st = LGCU_OK;
+  RasterArgs a;
+  if (!params || !fragments) return fail(LGCU_ERR_INVALID_ARGUMENT, "raster_gbuffer: null params / fragments");
+  if (fragmentPitchBytes < (uint64_t)width * sizeof(lgcu_fragment) || (fragmentPitchBytes % 16) != 0 || (reinterpret_cast<uintptr_t>(fragments) % 16) != 0)
+    return fail(LGCU_ERR_INVALID_ARGUMENT, "raster_gbuffer: fragment pitch %llu / alignment unusable for %u pixels", (unsigned long long)fragmentPitchBytes, width);
+  if (!fillRasterArgs(scene, params->viewMatrix, params->projMatrix, scratch, scratchBytes, width, height, &a, &st)) return st;
+  a.rows = rowRange(rows, 0, (int)height);
+  a.fragments = fragments;
+  a.fragmentPitch = fragmentPitchBytes;
+  a.depth = LevelView{nullptr, 0, 0, 0};
+  return cudaStatus(launchRaster(a, smCountOfCurrentDevice(), static_cast<cudaStream_t>(stream)), "raster_gbuffer");
+}
+
 // ------------------------------------------------------------------------------------------------------- peer-to-peer rows
 int lgcu_copy_rows(const lgcu_row_copy *copies, uint32_t count, void *stream) {
   if (!copies && count) return fail(LGCU_ERR_INVALID_ARGUMENT, "copy_rows: null list");

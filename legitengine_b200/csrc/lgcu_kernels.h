@@ -122,6 +122,19 @@ struct ChainsArgs { // everything of K3 + K4 that the front kernel leaves: blur 
   RowRange rows;  // base rows
 };
 
+struct RasterArgs { // ShadowPass / raster half of GBufferPass (k_raster.cu)
+  lgcu_mesh_scene scene; // device arrays
+  Mat4 viewProj;         // projMatrix * viewMatrix  (gBufferBuilder.vert:36, left-associative product)
+  int width, height;
+  RowRange rows;
+  void *scratch;            // rasterScratchBytes(scene.nTriangles, width, height)
+  lgcu_fragment *fragments; // G-buffer target: fragment buffer; nullptr selects the depth-only target
+  uint64_t fragmentPitch;
+  LevelView depth;          // shadow map (D32F)
+};
+uint64_t rasterScratchBytes(uint32_t nTriangles, uint32_t width, uint32_t height);
+cudaError_t launchRaster(const RasterArgs &a, int smCount, cudaStream_t s);
+
 constexpr int kMaxCopies = 64, kMaxFlags = 32;
 struct RowCopyArgs { // contiguous slabs (16-byte multiples), any of them possibly in a peer GPU's memory
   const void *src[kMaxCopies];

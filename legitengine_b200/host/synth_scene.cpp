@@ -331,3 +331,116 @@ void lgs_mat4_mul(const float *a_, const float *b_, float *out) {
 }
 
 } // extern "C"
+
+// ---- the same scene as an indexed triangle mesh (what the reference's Scene holds: src/Scene/Mesh.h:209-216 vertices, uint32
+// indices, one draw per object) for the rasterisation front end (lgcu_raster_*). Draw i uses objects[i]; boxes are stored in
+// object space (world / normalScale, unit normals) so that modelMatrix = scale(normalScale) reproduces the unnormalised world
+// normals of the ray-cast fragments. Box bottoms (coplanar with the ground) are not emitted.
+namespace {
+
+struct MeshBuilder {
+  std::vector<lgcu_vertex> vertices;
+  std::vector<uint32_t> indices;
+  std::vector<lgcu_draw> draws;
+  void beginDraw(uint32_t objectId) {
+    lgcu_draw d;
+    std::memset(&d, 0, sizeof(d));
+    d.firstIndex = uint32_t(indices.size());
+    d.objectId = objectId;
+    draws.push_back(d);
+  }
+  void endDraw() { draws.back().indexCount = uint32_t(indices.size()) - draws.back().firstIndex; }
+  // quad p0,p1,p2,p3 (in order around the face) with normal n, positions divided by `scale`
+  void quad(const double p[4][3], const double n[3], double scale) {
+    const uint32_t base = uint32_t(vertices.size());
+    for (int k = 0; k < 4; k++) {
+      lgcu_vertex v;
+      for (int c = 0; c < 3; c++) {
+        v.pos[c] = float(p[k][c] / scale);
+        v.normal[c] = float(n[c]);
+      }
+      v.uv[0] = (k == 1 || k == 2) ? 1.0f : 0.0f;
+      v.uv[1] = (k >= 2) ? 1.0f : 0.0f;
+      vertices.push_back(v);
+    }
+    const uint32_t idx[6] = {base, base + 1, base + 2, base, base + 2, base + 3};
+    indices.insert(indices.end(), idx, idx + 6);
+  }
+};
+
+MeshBuilder buildMesh(const Scene &sc) {
+  MeshBuilder mb;
+  const double R = kRoomHalf, Hh = kWallHeight;
+  {
+    const double p[4][3] = {{-R, 0, -R}, {R, 0, -R}, {R, 0, R}, {-R, 0, R}}, n[3] = {0, 1, 0};
+    mb.beginDraw(kGroundId); mb.quad(p, n, 1.0); mb.endDraw();
+  }
+  {
+    const double p[4][3] = {{-R, 0, R}, {R, 0, R}, {R, Hh, R}, {-R, Hh, R}}, n[3] = {0, 0, -1};
+    mb.beginDraw(kWallBackId); mb.quad(p, n, 1.0); mb.endDraw();
+  }
+  {
+    const double p[4][3] = {{-R, 0, -R}, {-R, 0, R}, {-R, Hh, R}, {-R, Hh, -R}}, n[3] = {1, 0, 0};
+    mb.beginDraw(kWallLeftId); mb.quad(p, n, 1.0); mb.endDraw();
+  }
+  {
+    const double p[4][3] = {{R, 0, -R}, {R, 0, R}, {R, Hh, R}, {R, Hh, -R}}, n[3] = {-1, 0, 0};
+    mb.beginDraw(kWallRightId); mb.quad(p, n, 1.0); mb.endDraw();
+  }
+  for (size_t i = 0; i < sc.boxes.size(); i++) {
+    const Box &b = sc.boxes[i];
+    const double s = double(float(b.normalScale));
+    const double *lo = b.lo, *hi = b.hi;
+    mb.beginDraw(kFirstBoxId + uint32_t(i));
+    {
+      const double p[4][3] = {{lo[0], hi[1], lo[2]}, {hi[0], hi[1], lo[2]}, {hi[0], hi[1], hi[2]}, {lo[0], hi[1], hi[2]}}, n[3] = {0, 1, 0};
+      mb.quad(p, n, s); // top
+    }
+    {
+      const double p[4][3] = {{lo[0], lo[1], lo[2]}, {hi[0], lo[1], lo[2]}, {hi[0], hi[1], lo[2]}, {lo[0], hi[1], lo[2]}}, n[3] = {0, 0, -1};
+      mb.quad(p, n, s); // z = lo
+    }
+    {
+      const double p[4][3] = {{lo[0], lo[1], hi[2]}, {hi[0], lo[1], hi[2]}, {hi[0], hi[1], hi[2]}, {lo[0], hi[1], hi[2]}}, n[3] = {0, 0, 1};
+      mb.quad(p, n, s); // z = hi
+    }
+    {
+      const double p[4][3] = {{lo[0], lo[1], lo[2]}, {lo[0], lo[1], hi[2]}, {lo[0], hi[1], hi[2]}, {lo[0], hi[1], lo[2]}}, n[3] = {-1, 0, 0};
+      mb.quad(p, n, s); // x = lo
+    }
+    {
+      const double p[4][3] = {{hi[0], lo[1], lo[2]}, {hi[0], lo[1], hi[2]}, {hi[0], hi[1], hi[2]}, {hi[0], hi[1], lo[2]}}, n[3] = {1, 0, 0};
+      mb.quad(p, n, s); // x = hi
+    }
+    mb.endDraw();
+  }
+  uint32_t tri = 0;
+  for (lgcu_draw &d : mb.draws) {
+    d.firstTriangle = tri;
+    tri += d.indexCount / 3;
+  }
+  return mb;
+}
+
+} // namespace
+
+extern "C" {
+
+// sizes of the mesh form of a scene with nBoxes boxes
+void lgs_scene_mesh_counts(uint32_t nBoxes, uint32_t *nVertices, uint32_t *nIndices, uint32_t *nDraws) {
+  const uint32_t quads = 4 + 5 * nBoxes;
+  *nVertices = 4 * quads;
+  *nIndices = 6 * quads;
+  *nDraws = kFirstBoxId + nBoxes;
+}
+
+int lgs_scene_mesh(uint64_t seed, uint32_t nBoxes, lgcu_vertex *vertices, uint32_t *indices, lgcu_draw *draws) {
+  Scene sc = buildScene(seed, nBoxes);
+  MeshBuilder mb = buildMesh(sc);
+  std::memcpy(vertices, mb.vertices.data(), mb.vertices.size() * sizeof(lgcu_vertex));
+  std::memcpy(indices, mb.indices.data(), mb.indices.size() * sizeof(uint32_t));
+  std::memcpy(draws, mb.draws.data(), mb.draws.size() * sizeof(lgcu_draw));
+  return LGCU_OK;
+}
+
+} // extern "C"

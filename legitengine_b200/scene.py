@@ -84,3 +84,27 @@ def scene_shadow_map(seed: int, m: FrameMatrices, n_boxes: int = DEFAULT_BOXES, 
 def make_scene(seed: int, width: int, height: int, n_boxes: int = DEFAULT_BOXES, camera=None, light=None, shadow_size: int = SHADOW_MAP_SIZE) -> Scene:
     m = frame_matrices(width, height, camera, light)
     return Scene(width, height, seed, m, scene_fragments(seed, width, height, m, n_boxes), scene_objects(seed, n_boxes), scene_shadow_map(seed, m, n_boxes, shadow_size))
+
+
+@dataclass
+class Mesh:
+    """The scene as the reference's Scene holds it (src/Scene/Scene.h, src/Scene/Mesh.h:209-216): input of lgcu_raster_*."""
+    vertices: np.ndarray  # (nv,) abi.VERTEX_DTYPE
+    indices: np.ndarray  # (ni,) uint32
+    draws: np.ndarray  # (nd,) abi.DRAW_DTYPE, firstTriangle filled
+    objects: np.ndarray  # (no,) abi.DRAW_CALL_DTYPE
+
+    @property
+    def triangle_count(self) -> int:
+        return int(self.draws["indexCount"].sum() // 3)
+
+
+def scene_mesh(seed: int, n_boxes: int = DEFAULT_BOXES) -> Mesh:
+    lib = abi.load_scene_lib()
+    nv, ni, nd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib.lgs_scene_mesh_counts(n_boxes, C.byref(nv), C.byref(ni), C.byref(nd))
+    vertices = np.zeros(nv.value, dtype=abi.VERTEX_DTYPE)
+    indices = np.zeros(ni.value, dtype=np.uint32)
+    draws = np.zeros(nd.value, dtype=abi.DRAW_DTYPE)
+    abi.check(lib.lgs_scene_mesh(seed, n_boxes, vertices.ctypes.data, indices.ctypes.data, draws.ctypes.data), "lgs_scene_mesh")
+    return Mesh(vertices, indices, draws, scene_objects(seed, n_boxes))

@@ -29,6 +29,13 @@ class Oracle:
         self.num_threads.restype = C.c_int
         self.set_num_threads = getattr(lib, f"{prefix}_set_num_threads")
         self.set_num_threads.argtypes = [C.c_int]
+        if kind == "port":  # rasterisation front end (oracle/raster_oracle.c): host scene arrays, host targets
+            lib.orc_raster_shadow_map.argtypes = [C.POINTER(abi.ShadowmapBuilderData), C.POINTER(abi.MeshScene), C.c_uint32, C.c_void_p, C.c_uint64]
+            lib.orc_raster_gbuffer.argtypes = [C.POINTER(abi.GBufferBuilderData), C.POINTER(abi.MeshScene), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, abi.ROWS]
+            lib.orc_vertex_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+            for fn in (lib.orc_raster_shadow_map, lib.orc_raster_gbuffer, lib.orc_vertex_stage):
+                fn.restype = C.c_int
+            self.raster_shadow_map, self.raster_gbuffer, self.vertex_stage = lib.orc_raster_shadow_map, lib.orc_raster_gbuffer, lib.orc_vertex_stage
 
 
 _port = None
@@ -60,4 +67,7 @@ def ref() -> Oracle:
         lib.ref_frame_matrices.restype = None
         lib.ref_mat4_inverse.argtypes = [f4, f4]
         lib.ref_mat4_mul.argtypes = [f4, f4, f4]
+        for fn in (lib.ref_gbuffer_vertex_stage, lib.ref_shadowmap_vertex_stage):  # (DrawCallData*, UBO*, vertices, n, out[n][10])
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+            fn.restype = C.c_int
     return _ref

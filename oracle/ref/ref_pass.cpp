@@ -273,6 +273,46 @@ extern "C" int ref_final_gather(const lgcu_final_gatherer_data *params, const lg
 }
 #endif
 
+#if REF_PASS == 8 || REF_PASS == 9
+// Vertex stage of GBufferPass (8: spirv/Common/gBufferBuilder.vert.spv) and ShadowPass (9: spirv/Common/shadowmapBuilder.vert.spv):
+// set 0 binding 0 = GBufferBuilderData / ShadowmapBuilderData, set 1 binding 0 = DrawCallData (SSVGIRenderer.h:72-92, 125-146);
+// inputs = the vertex declaration of src/Scene/Mesh.h:263-271. out = n x {vertWorldPos[3], vertWorldNormal[3], gl_Position[4]}.
+// Used to pin the vertex stage of oracle/raster_oracle.c.
+#if REF_PASS == 8
+extern "C" int ref_gbuffer_vertex_stage(const lgcu_draw_call_data *drawCall, const void *shaderData, const lgcu_vertex *vertices, uint32_t n, float *out) {
+#else
+extern "C" int ref_shadowmap_vertex_stage(const lgcu_draw_call_data *drawCall, const void *shaderData, const lgcu_vertex *vertices, uint32_t n, float *out) {
+#endif
+  const spirv_cross_interface *iface = spirv_cross_get_interface();
+  spirv_cross_shader_t *sh = iface->construct();
+  glm::vec4 position;
+  glm::vec3 pos, normal, worldPos, worldNormal;
+  glm::vec2 uv, outUv;
+  void *p0 = (void *)shaderData, *p1 = (void *)drawCall;
+  spirv_cross_set_builtin(sh, SPIRV_CROSS_BUILTIN_POSITION, &position, sizeof(position));
+  spirv_cross_set_resource(sh, 0, 0, &p0, sizeof(p0));
+  spirv_cross_set_resource(sh, 1, 0, &p1, sizeof(p1));
+  spirv_cross_set_stage_input(sh, 0, &pos, sizeof(pos));
+  spirv_cross_set_stage_input(sh, 1, &normal, sizeof(normal));
+  spirv_cross_set_stage_input(sh, 2, &uv, sizeof(uv));
+  spirv_cross_set_stage_output(sh, 0, &worldPos, sizeof(worldPos));
+  spirv_cross_set_stage_output(sh, 1, &worldNormal, sizeof(worldNormal));
+  spirv_cross_set_stage_output(sh, 2, &outUv, sizeof(outUv));
+  for (uint32_t i = 0; i < n; i++) {
+    pos = glm::vec3(vertices[i].pos[0], vertices[i].pos[1], vertices[i].pos[2]);
+    normal = glm::vec3(vertices[i].normal[0], vertices[i].normal[1], vertices[i].normal[2]);
+    uv = glm::vec2(vertices[i].uv[0], vertices[i].uv[1]);
+    iface->invoke(sh);
+    float *o = out + 10 * i;
+    o[0] = worldPos.x; o[1] = worldPos.y; o[2] = worldPos.z;
+    o[3] = worldNormal.x; o[4] = worldNormal.y; o[5] = worldNormal.z;
+    o[6] = position.x; o[7] = position.y; o[8] = position.z; o[9] = position.w;
+  }
+  iface->destruct(sh);
+  return LGCU_OK;
+}
+#endif
+
 #if REF_PASS == 1
 extern "C" int ref_num_threads(void) { return omp_get_max_threads(); }
 extern "C" void ref_set_num_threads(int n) { omp_set_num_threads(n); }
