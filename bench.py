@@ -5,9 +5,13 @@ gather) on B200, measured as BASELINE.json's metric: frame ms and Mpix/s, with t
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 4k|8k|1080p|WxH] [--impl ours|reference]
 
 One "step" = one frame of the workload through the C++ rendergraph harness (liblegit_cuda.so -> liblgcu.so kernels).
-  value : whole-job Mpix/s with the rasterised scene already resident in HBM (CUDA-graph replay of the fused frame)
-  e2e   : same frame driven from HOST buffers: every step copies the fragment buffer host->device from pinned memory,
-          renders, and copies the BGRA8 swapchain image device->host, all inside the timed region
+  value : whole-job Mpix/s with the rasterised scene (SURVEY.md §8d's per-pixel fragment buffer) already resident in HBM
+          (CUDA-graph replay of the fused frame)
+  e2e   : the frame as the reference's RenderFrame receives it — the SCENE (vertex / index buffers, draw list, per-object
+          constants) in HOST memory: every step copies the scene host->device from pinned memory, rasterises it on the device
+          (ShadowPass + GBufferRasterPass), renders the frame and copies the BGRA8 swapchain image device->host, all inside the
+          timed region. value_from_mesh is the same frame with the scene resident. e2e_fragments is the other host-buffer form:
+          the pre-rasterised 32 B/px fragment buffer uploaded every step (PCIe-bound).
 N > 1   : one process per GPU (torchrun); independent frames per GPU (BASELINE configs[4], "weak"), no data-path collective
 --impl reference : the reference's own SPIR-V passes on the host cores (oracle/_ref, else the C port), bounded sample.
 The CPU oracle is used here ONLY for the cpu_baseline / reference legs — never on the product path.
@@ -301,6 +305,43 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return ms
 
     e2e_steps = args.e2e_steps or min(args.steps, 60)
+    e2e_frag_ms = e2e_timed(e2e_steps, max(3, in_flight))
+    e2e_frag_value = world * npx / (e2e_frag_ms / e2e_steps * 1e-3) / 1e6
+
+    # --- the same frame from the scene in the reference's form (mesh): every slot switches to mesh input and re-captures
+    mesh = scene.scene_mesh(seed)
+    pinned = {}
+    for name in ("vertices", "indices", "draws", "objects"):
+        a = getattr(mesh, name)
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        v = t.numpy().view(a.dtype)
+        v[...] = a
+        pinned[name] = (t, v)
+    mesh_pinned = scene.Mesh(*(pinned[n][1] for n in ("vertices", "indices", "draws", "objects")))
+    mesh_bytes = sum(pinned[n][0].numel() for n in pinned)
+    for r_i, s_i, _ in slots:
+        r_i.upload_mesh(mesh_pinned)
+        r_i.render_frame(mode, 0, gi_flags)
+        r_i.sync()
+    pass_ms_mesh = {}
+    for _ in range(prof_frames):
+        r.render_frame(mode, 0, gi_flags, profile=True)
+        r.sync()
+        for name, ms in r.profile():
+            pass_ms_mesh[name] = pass_ms_mesh.get(name, 0.0) + ms / prof_frames
+    for r_i, _, _ in slots:
+        r_i.capture_frame(mode, 0, gi_flags)
+    kernels_per_frame_mesh = r.captured_kernel_count()
+    mesh_ms_total, _ = timed(r.replay_frame, args.steps, max(args.warmup, 3))
+    mesh_ms_per_step = mesh_ms_total / args.steps
+
+    def e2e_step():  # noqa: F811 — scene in, swapchain out
+        r_i, _, swap_i = slots[counter[0] % in_flight]
+        counter[0] += 1
+        r_i.upload_mesh(mesh_pinned)
+        r_i.replay_frame()
+        r_i.download_swapchain(swap_i.data_ptr(), W * 4)
+
     e2e_ms = e2e_timed(e2e_steps, max(3, in_flight))
     e2e_value = world * npx / (e2e_ms / e2e_steps * 1e-3) / 1e6
 
@@ -330,13 +371,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "storage": "RGBA16F / RG32F / D32F / BGRA8 images exactly as the reference allocates them",
             },
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms / e2e_steps, "frames_in_flight": in_flight},
+            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": mesh_bytes, "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps, "frames_in_flight": in_flight,
+                    "input": "scene as the reference holds it (vertex + index buffers, draw list, per-object constants: %d triangles), uploaded from pinned host "
+                             "memory every step and rasterised on the device (ShadowPass + GBufferRasterPass); output: BGRA8 swapchain image to pinned host memory"
+                             % mesh.triangle_count},
+            "e2e_fragments": {"value": e2e_frag_value, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4, "steps": e2e_steps,
+                              "ms_per_step": e2e_frag_ms / e2e_steps, "frames_in_flight": in_flight,
+                              "input": "pre-rasterised 32 B/px fragment buffer uploaded every step (PCIe-bound)"},
+            "value_from_mesh": {"value": world * npx / (mesh_ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": mesh_ms_per_step,
+                                "kernels_per_frame": kernels_per_frame_mesh, "note": "scene resident; frame = ShadowPass + GBufferRasterPass + the passes of `value`"},
             "gpu_launches": kernels_per_frame * args.steps,
             "kernels_per_frame": kernels_per_frame,
             "roofline": roofline,
             "roofline_frame": roofline_frame,
             "pass_ms": {k: round(v, 4) for k, v in pass_ms.items()},
+            "pass_ms_mesh": {k: round(v, 4) for k, v in pass_ms_mesh.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             sw, sh = W // 2, H // 2

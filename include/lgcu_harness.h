@@ -39,6 +39,17 @@ int lgh_upload_fragments(lgh_renderer *r, const lgcu_fragment *hostFragments, ui
 int lgh_upload_objects(lgh_renderer *r, const lgcu_draw_call_data *hostObjects, uint32_t count);
 int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t size);
 
+/* Scene as the reference's Scene holds it (src/Scene/Scene.h:141-147, src/Scene/Mesh.h:244-262): vertex / index buffers, the draw
+ * list (one entry per Scene::IterateObjects callback, firstTriangle filled by lgcu_raster_prepare_draws) and the per-object
+ * constants. HOST arrays, copied asynchronously on the renderer's stream. After this call frames start from the mesh: "ShadowPass"
+ * and "GBufferRasterPass" rasterise it on the device (lgcu_raster_shadow_map / lgcu_raster_gbuffer) and the fragment / light-depth
+ * uploads are not used. A frame captured before the first lgh_upload_mesh, or before one that grew the scene, must be re-captured;
+ * re-uploading a scene of the same size (per-frame object constants, animated vertices) keeps the captured frame valid.
+ * lgh_use_mesh(r, 0) switches back to the pre-rasterised inputs. */
+int lgh_upload_mesh(lgh_renderer *r, const lgcu_vertex *hostVertices, uint32_t nVertices, const uint32_t *hostIndices, uint32_t nIndices,
+                    const lgcu_draw *hostDraws, uint32_t nDraws, const lgcu_draw_call_data *hostObjects, uint32_t nObjects);
+int lgh_use_mesh(lgh_renderer *r, uint32_t enable);
+
 /* One frame: SSVGIRenderer::RenderFrame + RenderGraph::Execute. rows may be NULL (whole frame; required for pass-granular).
  * profile != 0 records per-pass GPU events (read them with lgh_get_profile after lgh_sync). */
 int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile);

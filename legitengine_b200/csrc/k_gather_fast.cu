@@ -157,7 +157,28 @@ __device__ __forceinline__ float4 mulMat4Exact(const Mat4 &M, float x, float y, 
 }
 __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 
-template <bool kQuads, bool kSmem, int kMinBlocks>
+// One march sample in flight (software-pipelined variant): the footprints of both LOD levels and the raw quad taps, loaded one
+// step ahead so that the L1/L2 latency of step k+1 overlaps the horizon test and the hit body of step k.
+struct PendingSample {
+  Footprint f0, f1;
+  float4 q0, q1;
+};
+__device__ __forceinline__ PendingSample issueSample(const StepRow &st, const DirEntry &de, float px, float py, const float4 *__restrict__ quads) {
+  PendingSample p;
+  const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
+  p.f0 = footprint(st.g0, sx, sy);
+  p.q0 = __ldg(quads + (unsigned)(st.g0.quadOfs + (p.f0.iy + 1) * st.g0.quadPitch + (p.f0.ix + 1)));
+  p.f1 = p.f0;
+  p.q1 = p.q0;
+  if (st.frac > 0.0f) { // uniform branch
+    p.f1 = footprint(st.g1, sx, sy);
+    p.q1 = __ldg(quads + (unsigned)(st.g1.quadOfs + (p.f1.iy + 1) * st.g1.quadPitch + (p.f1.ix + 1)));
+  }
+  return p;
+}
+__device__ __forceinline__ float bilerpQuad(const float4 &q, const Footprint &f) { return lerpf(lerpf(q.x, q.y, f.a), lerpf(q.z, q.w, f.a), f.b); }
+
+template <bool kQuads, bool kSmem, int kMinBlocks, bool kPipe = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
                                                                           const float4 *__restrict__ quads) {
   __shared__ StepRow sRows[kSmem ? kMaxSteps : 1];
@@ -243,17 +264,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const _
       const float xRd = tb.raySign * dotf(eye, Rd), yRd = tb.raySign * dotf(tang, Rd);
 
       const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
-#pragma unroll 1
-      for (int k = 0; k < warpIters; k++) { // :214
-        const StepRow &st = rows[k];
-        const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-        const Footprint f0 = footprint(st.g0, sx, sy);
-        Footprint f1 = f0;
-        float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
-        if (st.frac > 0.0f) { // uniform branch
-          f1 = footprint(st.g1, sx, sy);
-          z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
-        }
+      // horizon test + hit body of one march sample whose depth z is known (:241-263)
+      auto shade = [&](int k, const StepRow &st, const Footprint &f0, const Footprint &f1, float z) {
         const float zs = z * fastRsqrt(fmaf(st.off, fmaf(st.off, q2, q1), q0)); // z / |R(s)|
         const float hx = fmaf(zs, fmaf(st.off, xRd, xR0), xE); // dot(eye, P - C)      :241-252
         const float hy = fmaf(zs, fmaf(st.off, yRd, yR0), yE); // dot(tangent, P - C)
@@ -265,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const _
           const float inv = fastRcp(fmaxf(fmaf(hx, hx, hy * hy), 1e-37f));
           const float c2 = (hx * hx - hy * hy) * inv, s2 = 2.0f * hx * hy * inv;
           const float hc = eN4 * (c2 - c2m) + tN4 * (((2.0f * maxH - 2.0f * h) - s2m) + s2); // :44-49
+          const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
           const float su = sx * invVpx, sv = sy * invVpy;
           // product of the four saturates of :220-228 (at most one per axis is below 1)
           const float side = saturatef(fminf(su, 1.0f - su) * 10.0f) * saturatef(fminf(sv, 1.0f - sv) * 10.0f);
@@ -285,6 +298,40 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const _
           s2m = s2;
           mx = hx;
           my = hy;
+        }
+      };
+      if (kPipe && kQuads) {
+        // software-pipelined march, two steps per trip with ping-pong sample registers: the quad loads of step k+1 are in flight
+        // while step k runs its horizon test and hit body
+        auto consume = [&](int k, const PendingSample &ps) {
+          const StepRow &st = rows[k];
+          float z = bilerpQuad(ps.q0, ps.f0);
+          if (st.frac > 0.0f) z = fmaf(st.frac, bilerpQuad(ps.q1, ps.f1) - z, z); // :240
+          shade(k, st, ps.f0, ps.f1, z);
+        };
+        PendingSample sa, sb;
+        if (warpIters > 0) sa = issueSample(rows[0], de, px, py, quads);
+#pragma unroll 1
+        for (int k = 0; k < warpIters; k += 2) { // :214 (every branch here is warp-uniform)
+          if (k + 1 < warpIters) sb = issueSample(rows[k + 1], de, px, py, quads);
+          consume(k, sa);
+          if (k + 1 >= warpIters) break;
+          if (k + 2 < warpIters) sa = issueSample(rows[k + 2], de, px, py, quads);
+          consume(k + 1, sb);
+        }
+      } else {
+#pragma unroll 1
+        for (int k = 0; k < warpIters; k++) { // :214
+          const StepRow &st = rows[k];
+          const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
+          const Footprint f0 = footprint(st.g0, sx, sy);
+          Footprint f1 = f0;
+          float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
+          if (st.frac > 0.0f) { // uniform branch
+            f1 = footprint(st.g1, sx, sy);
+            z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
+          }
+          shade(k, st, f0, f1, z);
         }
       }
       const float amb = -0.01f * cSum;
@@ -477,6 +524,16 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
     gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, q);
   else if (variant == 3)
     gatherFastKernel<true, true, 3><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 4)
+    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 5)
+    gatherFastKernel<true, false, 4, true><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 6)
+    gatherFastKernel<true, true, 3, true><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 7)
+    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, q);
+  else if (variant == 8)
+    gatherFastKernel<true, true, 2, true><<<grid, kThreads, 0, s>>>(a, f, q);
   else
     gatherFastKernel<true, false, 4><<<grid, kThreads, 0, s>>>(a, f, q);
   return cudaGetLastError();

@@ -40,6 +40,8 @@ def load_harness() -> C.CDLL:
         lib.lgh_upload_fragments.argtypes = [R, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
         lib.lgh_upload_objects.argtypes = [R, C.c_void_p, C.c_uint32]
         lib.lgh_upload_light_depth.argtypes = [R, C.c_void_p, C.c_uint32]
+        lib.lgh_upload_mesh.argtypes = [R, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        lib.lgh_use_mesh.argtypes = [R, C.c_uint32]
         lib.lgh_render_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         lib.lgh_render_stages.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         H64 = C.c_ubyte * 64
@@ -109,6 +111,15 @@ class Renderer:
         self.upload_objects(sc.objects.ctypes.data, len(sc.objects))
         self.upload_light_depth(np.ascontiguousarray(sc.shadow_map).ctypes.data, sc.shadow_map.shape[0])
         self.sync()
+
+    def upload_mesh(self, mesh) -> None:
+        """Scene in the reference's form (legitengine_b200.scene.Mesh, or anything with the same four arrays — e.g. views of pinned
+        memory): frames then start from the mesh (ShadowPass + GBufferRasterPass rasterise it on the device). Asynchronous."""
+        _check(self.lib.lgh_upload_mesh(self.handle, C.c_void_p(mesh.vertices.ctypes.data), len(mesh.vertices), C.c_void_p(mesh.indices.ctypes.data), len(mesh.indices),
+                                        C.c_void_p(mesh.draws.ctypes.data), len(mesh.draws), C.c_void_p(mesh.objects.ctypes.data), len(mesh.objects)), "lgh_upload_mesh")
+
+    def use_mesh(self, enable: bool) -> None:
+        _check(self.lib.lgh_use_mesh(self.handle, 1 if enable else 0), "lgh_use_mesh")
 
     # -- frames --------------------------------------------------------------------------------------------------
     @staticmethod

@@ -43,6 +43,10 @@ struct lgh_renderer {
   std::unique_ptr<Buffer> fragments, objects, lightDepth;
   uint32_t objectCapacity = 0, objectCount = 0, lightDepthSize = 0;
   std::unique_ptr<Scene> scene;
+  // mesh form of the scene (lgh_upload_mesh): device copies of the reference's vertex / index buffers, draw list, per-object constants
+  std::unique_ptr<Buffer> meshVertices, meshIndices, meshDraws, meshObjects, rasterScratch;
+  lgcu_mesh_scene meshDesc{};
+  bool useMesh = false;
 
   std::unique_ptr<ImageData> swapchainImage;
   std::unique_ptr<ImageView> swapchainView;
@@ -68,6 +72,14 @@ struct lgh_renderer {
     if (!scene) scene.reset(new Scene(core->GetRenderGraph(), fragments.get(), fragmentPitch(), objects.get(), objectCount, lightDepth.get(), lightDepthSize));
     scene->objectsCount = objectCount;
     scene->lightDepthSize = lightDepthSize;
+    if (useMesh)
+      scene->SetMesh(core->GetRenderGraph(), meshDesc, rasterScratch.get());
+    else
+      scene->ClearMesh();
+  }
+
+  static void fit(std::unique_ptr<Buffer> &b, size_t bytes) {
+    if (!b || b->GetSize() < bytes) b.reset(new Buffer(bytes + bytes / 4));
   }
 
   void declareAndExecute(uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, bool profile, uint32_t stages = FrameOptions::StageAll) {
@@ -206,6 +218,51 @@ int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t siz
     r->ensureScene();
     CudaCheck(cudaMemcpyAsync(r->lightDepth->GetHandle(), hostDepth, size_t(size) * size * 4, cudaMemcpyHostToDevice, r->stream), "upload light depth");
   })
+}
+
+int lgh_upload_mesh(lgh_renderer *r, const lgcu_vertex *hostVertices, uint32_t nVertices, const uint32_t *hostIndices, uint32_t nIndices,
+                    const lgcu_draw *hostDraws, uint32_t nDraws, const lgcu_draw_call_data *hostObjects, uint32_t nObjects) {
+  if (!r || !hostVertices || !hostIndices || !hostDraws || !hostObjects || !nVertices || !nIndices || !nDraws || !nObjects)
+    return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_mesh: null / empty argument");
+  uint64_t triangles = 0;
+  for (uint32_t i = 0; i < nDraws; i++) {
+    const lgcu_draw &d = hostDraws[i];
+    if (d.indexCount % 3 != 0 || uint64_t(d.firstIndex) + d.indexCount > nIndices || d.objectId >= nObjects || d.firstTriangle != triangles)
+      return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_mesh: draw %u is out of range or its firstTriangle is not filled (lgcu_raster_prepare_draws)", i);
+    triangles += d.indexCount / 3;
+  }
+  if (triangles == 0 || triangles > 0x7fffffffull) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_upload_mesh: %llu triangles", (unsigned long long)triangles);
+  LGH_TRY({
+    // growing a buffer invalidates a captured frame (it holds the old addresses); the caller re-captures after a scene change
+    lgh_renderer::fit(r->meshVertices, size_t(nVertices) * sizeof(lgcu_vertex));
+    lgh_renderer::fit(r->meshIndices, size_t(nIndices) * 4);
+    lgh_renderer::fit(r->meshDraws, size_t(nDraws) * sizeof(lgcu_draw));
+    lgh_renderer::fit(r->meshObjects, size_t(nObjects) * sizeof(lgcu_draw_call_data));
+    const uint64_t frameScratch = lgcu_raster_scratch_bytes(uint32_t(triangles), r->width, r->height);
+    const uint64_t shadowScratch = lgcu_raster_scratch_bytes(uint32_t(triangles), 1024, 1024); // SSVGIRenderer.h:402
+    lgh_renderer::fit(r->rasterScratch, size_t(frameScratch > shadowScratch ? frameScratch : shadowScratch));
+    CudaCheck(cudaMemcpyAsync(r->meshVertices->GetHandle(), hostVertices, size_t(nVertices) * sizeof(lgcu_vertex), cudaMemcpyHostToDevice, r->stream), "upload vertices");
+    CudaCheck(cudaMemcpyAsync(r->meshIndices->GetHandle(), hostIndices, size_t(nIndices) * 4, cudaMemcpyHostToDevice, r->stream), "upload indices");
+    CudaCheck(cudaMemcpyAsync(r->meshDraws->GetHandle(), hostDraws, size_t(nDraws) * sizeof(lgcu_draw), cudaMemcpyHostToDevice, r->stream), "upload draws");
+    CudaCheck(cudaMemcpyAsync(r->meshObjects->GetHandle(), hostObjects, size_t(nObjects) * sizeof(lgcu_draw_call_data), cudaMemcpyHostToDevice, r->stream), "upload objects");
+    r->meshDesc.vertices = static_cast<const lgcu_vertex *>(r->meshVertices->GetHandle());
+    r->meshDesc.indices = static_cast<const uint32_t *>(r->meshIndices->GetHandle());
+    r->meshDesc.draws = static_cast<const lgcu_draw *>(r->meshDraws->GetHandle());
+    r->meshDesc.objects = static_cast<const lgcu_draw_call_data *>(r->meshObjects->GetHandle());
+    r->meshDesc.nVertices = nVertices;
+    r->meshDesc.nIndices = nIndices;
+    r->meshDesc.nDraws = nDraws;
+    r->meshDesc.nObjects = nObjects;
+    r->meshDesc.nTriangles = uint32_t(triangles);
+    r->useMesh = true;
+  })
+}
+
+int lgh_use_mesh(lgh_renderer *r, uint32_t enable) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_use_mesh: null renderer");
+  if (enable && !r->meshVertices) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_use_mesh: no mesh uploaded");
+  r->useMesh = enable != 0;
+  return LGCU_OK;
 }
 
 int lgh_render_frame(lgh_renderer *r, uint32_t mode, int32_t denoiserRadius, uint32_t giFlags, const lgcu_rows *rows, uint32_t profile) {

@@ -6,10 +6,14 @@
 // calls one lgcu_* entry point where the reference binds a pipeline + descriptor set and draws a full-screen quad.
 //
 // What differs, and why:
-//  * Scene. The reference rasterises meshes (Scene::IterateObjects, :84-102, :138-156). Rasterisation is outside the
-//    hot path, so the scene arrives already rasterised: a per-pixel fragment buffer, the
-//    per-draw-call constants and the light's depth map. "ShadowPass" copies that depth map into the shadowMap image;
-//    "GBufferPass" runs the fragment stage (lgcu_gbuffer_resolve) over the fragment buffer.
+//  * Scene. The reference rasterises meshes (Scene::IterateObjects, :84-102, :138-156) with the fixed-function rasteriser. Here
+//    a Scene comes in one of two forms:
+//      - mesh (Scene::SetMesh): vertex / index buffers + draw list + per-object constants, like the reference's Scene.
+//        "ShadowPass" rasterises the light's depth map (lgcu_raster_shadow_map) and "GBufferRasterPass" writes the per-pixel
+//        fragment buffer (lgcu_raster_gbuffer) that the fragment stage then reads;
+//      - already rasterised (§8d's synthetic input): the fragment buffer, the per-draw-call constants and the light's depth map
+//        arrive from outside; "ShadowPass" copies that depth map into the shadowMap image.
+//    In both forms "GBufferPass" runs the fragment stage (lgcu_gbuffer_resolve) over the fragment buffer.
 //  * FrameOptions::mode == Fused replaces groups of passes by the fused entry points (frame front = K1+K2+level-0 blur+mips 1..4,
 //    frame chains = remaining blur/mip work, packed GI gather, K6+K7): identical images, 6 launches instead of 46 passes.
 //    PassGranular is the 1:1 pass list (47 passes incl. shadow).
@@ -38,10 +42,29 @@ struct Scene {
     objectsProxy = graph->AddExternalBuffer(objects);
     lightDepthProxy = graph->AddExternalBuffer(lightDepth);
   }
+  // Mesh form: the buffers of desc are device memory owned by the caller; scratch must hold lgcu_raster_scratch_bytes for both the
+  // viewport and the shadow map. The draw-call constants the fragment stage reads are desc.objects.
+  void SetMesh(RenderGraph *graph, const lgcu_mesh_scene &desc, Buffer *rasterScratch_) {
+    mesh = desc;
+    if (rasterScratch != rasterScratch_ || !rasterScratchProxy.IsAttached()) {
+      rasterScratch = rasterScratch_;
+      rasterScratchProxy = graph->AddExternalBuffer(rasterScratch);
+    }
+    hasMesh = true;
+  }
+  void ClearMesh() { hasMesh = false; }
+  const lgcu_draw_call_data *DrawCallData(Buffer *resolvedObjects) const {
+    return hasMesh ? mesh.objects : static_cast<const lgcu_draw_call_data *>(resolvedObjects->GetHandle());
+  }
+  uint32_t DrawCallCount() const { return hasMesh ? mesh.nObjects : objectsCount; }
   Buffer *fragments, *objects, *lightDepth;
   uint64_t fragmentPitch;
   uint32_t objectsCount, lightDepthSize;
   RenderGraph::BufferProxyUnique fragmentsProxy, objectsProxy, lightDepthProxy;
+  bool hasMesh = false;
+  lgcu_mesh_scene mesh{};
+  Buffer *rasterScratch = nullptr;
+  RenderGraph::BufferProxyUnique rasterScratchProxy;
 };
 
 struct FrameOptions {
@@ -90,9 +113,27 @@ public:
     auto rowsOf = [useRows](const PassData &pd) -> const lgcu_rows * { return useRows ? &pd.rowsStorage : nullptr; };
 
     const uint32_t stages = options.mode == FrameOptions::Mode::Fused ? options.stages : uint32_t(FrameOptions::StageAll);
-    // rendering shadow map (:61-104) — the light's depth arrives rasterised with the scene
+    // rendering shadow map (:61-104)
     vk::Extent2D shadowMapExtent(res->shadowMap.baseSize.x, res->shadowMap.baseSize.y);
-    if (stages & FrameOptions::StageFront)
+    if ((stages & FrameOptions::StageFront) && scene->hasMesh)
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                       .SetDepthAttachment(res->shadowMap.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
+                       .SetStorageBuffers({scene->rasterScratchProxy->Id()})
+                       .SetRenderAreaExtent(shadowMapExtent)
+                       .SetProfilerInfo(Colors::amethyst, "ShadowPass")
+                       .SetRecordFunc([passData](RenderGraph::RenderPassContext passContext) {
+                         passData.memoryPool->BeginSet();
+                         auto shaderDataBuffer = passData.memoryPool->GetUniformBufferData<lgcu_shadowmap_builder_data>("ShadowmapBuilderData");
+                         shaderDataBuffer->lightViewMatrix = passData.lightViewMatrix; // :77-78
+                         shaderDataBuffer->lightProjMatrix = passData.lightProjMatrix;
+                         passData.memoryPool->EndSet();
+                         Buffer *scratch = passContext.GetBuffer(passData.scene->rasterScratchProxy->Id());
+                         // Scene::IterateObjects + drawIndexed per object (:84-102) = the draw list of the mesh scene
+                         LgcuCheck(lgcu_raster_shadow_map(shaderDataBuffer, &passData.scene->mesh, scratch->GetHandle(), scratch->GetSize(),
+                                                          passContext.GetDepthAttachment()->GetDesc(), passContext.GetStream()),
+                                   "ShadowPass");
+                       }));
+    else if (stages & FrameOptions::StageFront) // the light's depth arrives rasterised with the scene
       graph->AddPass(RenderGraph::RenderPassDesc()
                        .SetDepthAttachment(res->shadowMap.imageViewProxy->Id(), vk::AttachmentLoadOp::eClear)
                        .SetStorageBuffers({scene->lightDepthProxy->Id()})
@@ -136,6 +177,24 @@ public:
       return clear;
     };
 
+    // rendering gbuffer (:106-158), raster half: vertex stage + rasteriser + depth test -> per-pixel fragment buffer
+    if (scene->hasMesh && (stages & FrameOptions::StageFront)) {
+      const uint32_t vw = viewportExtent.width, vh = viewportExtent.height;
+      graph->AddPass(RenderGraph::RenderPassDesc()
+                         .SetStorageBuffers({scene->fragmentsProxy->Id(), scene->rasterScratchProxy->Id()})
+                         .SetRenderAreaExtent(viewportExtent)
+                         .SetProfilerInfo(Colors::belizeHole, "GBufferRasterPass")
+                         .SetRecordFunc([passData, fillGBufferData, rowsOf, vw, vh](RenderGraph::RenderPassContext passContext) {
+                           auto shaderDataBuffer = fillGBufferData(passData);
+                           Scene *sc = passData.scene;
+                           Buffer *scratch = passContext.GetBuffer(sc->rasterScratchProxy->Id());
+                           LgcuCheck(lgcu_raster_gbuffer(shaderDataBuffer, &sc->mesh, scratch->GetHandle(), scratch->GetSize(), vw, vh,
+                                                         static_cast<lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()), sc->fragmentPitch,
+                                                         rowsOf(passData), passContext.GetStream()),
+                                     "GBufferRasterPass");
+                         }));
+    }
+
     if (options.mode == FrameOptions::Mode::PassGranular) {
       // rendering gbuffer (:106-158): fragment stage over the rasterised fragments
       graph->AddPass(RenderGraph::RenderPassDesc()
@@ -152,8 +211,8 @@ public:
                            auto shaderDataBuffer = fillGBufferData(passData);
                            const lgcu_clear_values clear = clearOf(passContext);
                            Scene *sc = passData.scene;
-                           LgcuCheck(lgcu_gbuffer_resolve(shaderDataBuffer, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
-                                                          sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
+                           LgcuCheck(lgcu_gbuffer_resolve(shaderDataBuffer, sc->DrawCallData(passContext.GetBuffer(sc->objectsProxy->Id())),
+                                                          sc->DrawCallCount(), static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
                                                           sc->fragmentPitch, &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
                                                           passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(),
                                                           passContext.GetDepthAttachment()->GetDesc(), rowsOf(passData), passContext.GetStream()),
@@ -208,8 +267,8 @@ public:
                            auto lightData = fillLightData(passData);
                            const lgcu_clear_values clear = clearOf(passContext);
                            Scene *sc = passData.scene;
-                           LgcuCheck(lgcu_frame_front(gbufferData, lightData, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
-                                                      sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
+                           LgcuCheck(lgcu_frame_front(gbufferData, lightData, sc->DrawCallData(passContext.GetBuffer(sc->objectsProxy->Id())),
+                                                      sc->DrawCallCount(), static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()),
                                                       sc->fragmentPitch, &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
                                                       passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(),
                                                       passContext.GetDepthAttachment()->GetDesc(),
@@ -251,8 +310,8 @@ public:
                            const lgcu_clear_values clear = clearOf(passContext);
                            Scene *sc = passData.scene;
                            LgcuCheck(lgcu_gbuffer_direct_light(
-                                         gbufferData, lightData, static_cast<const lgcu_draw_call_data *>(passContext.GetBuffer(sc->objectsProxy->Id())->GetHandle()),
-                                         sc->objectsCount, static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()), sc->fragmentPitch,
+                                         gbufferData, lightData, sc->DrawCallData(passContext.GetBuffer(sc->objectsProxy->Id())),
+                                         sc->DrawCallCount(), static_cast<const lgcu_fragment *>(passContext.GetBuffer(sc->fragmentsProxy->Id())->GetHandle()), sc->fragmentPitch,
                                          &clear, passContext.GetColorAttachment(0)->GetDesc(), passContext.GetColorAttachment(1)->GetDesc(),
                                          passContext.GetColorAttachment(2)->GetDesc(), passContext.GetColorAttachment(3)->GetDesc(), passContext.GetDepthAttachment()->GetDesc(),
                                          passContext.GetImageView(this->viewportResources->shadowMap.imageViewProxy->Id())->GetDesc(),

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Time the GI gather kernel variant selected by LGCU_GATHER_VARIANT (development switch in csrc/k_gather_fast.cu) on one 4K frame:
+prints the per-pass GPU times of the fused frame (mean of N profiled frames) as one JSON line."""
+import json
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+import torch  # noqa: E402
+
+from legitengine_b200 import abi, harness, scene  # noqa: E402
+
+W, H = (3840, 2160) if len(sys.argv) < 3 else (int(sys.argv[1]), int(sys.argv[2]))
+m = scene.frame_matrices(W, H)
+frags = scene.scene_fragments(0xC0FFEE, W, H, m)
+objects = scene.scene_objects(0xC0FFEE)
+shadow = scene.scene_shadow_map(0xC0FFEE, m)
+r = harness.Renderer(W, H)
+r.upload_fragments(frags.ctypes.data, frags.strides[0])
+r.upload_objects(objects.ctypes.data, len(objects))
+r.upload_light_depth(shadow.ctypes.data, 1024)
+r.sync()
+for _ in range(3):
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
+r.sync()
+acc, n = {}, 10
+for _ in range(n):
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT, profile=True)
+    r.sync()
+    for name, ms in r.profile():
+        acc[name] = acc.get(name, 0.0) + ms / n
+print(json.dumps({"variant": os.environ.get("LGCU_GATHER_VARIANT", "0"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
