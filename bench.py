@@ -476,6 +476,21 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         e2e_ms, _ = timed(e2e_step, e2e_steps, 3)
         recv_all = torch.tensor([received], device="cuda", dtype=torch.int64)
         dist.all_reduce(recv_all)
+        # per-rank, per-stage GPU time of un-captured frames (events between the stages on every rank): shows where a strip waits
+        stage_ms = None
+        if args.transport == "p2p":
+            n_marks, prof_frames = len(sr.STAGE_MARKS), 8
+            acc = torch.zeros(n_marks - 1, device="cuda")
+            for i in range(prof_frames + 2):
+                marks = []
+                sr.render(gi_flags, marks=marks)
+                torch.cuda.synchronize()
+                if i >= 2:
+                    acc += torch.tensor([marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks - 1)], device="cuda") / prof_frames
+            dist.barrier()
+            every = [torch.zeros_like(acc) for _ in range(world)]
+            dist.all_gather(every, acc)
+            stage_ms = {name: [round(float(e[j]), 4) for e in every] for j, name in enumerate(sr.STAGE_MARKS[1:])}
     if rank == 0:
         npx = W * H
         peak, peak_src = measured_peak_gbs()
@@ -496,6 +511,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": 5 * args.steps * world,
             "kernels_per_frame": 5,
+            "stage_ms_per_rank": stage_ms,
             "roofline_frame": {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                                "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes": frame_bytes,
                                "note": "whole frame over all GPUs, pass-granular algorithmic bytes; peak = N x measured single-GPU HBM copy bandwidth"},

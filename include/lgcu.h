@@ -96,6 +96,10 @@ typedef struct lgcu_indirect_lighting_data { lgcu_mat4 viewMatrix, projMatrix; f
 typedef struct lgcu_denoiser_data { lgcu_mat4 viewMatrix, projMatrix; float viewportExtent[4]; int32_t radius; } lgcu_denoiser_data;
 /* SSVGIRenderer.h:509-513, SH/Common/finalGatherer.frag:4-8 */
 typedef struct lgcu_final_gatherer_data { lgcu_mat4 viewMatrix, projMatrix; } lgcu_final_gatherer_data;
+/* InterleaveBuilder.h:99-123 (DeinterleaveShader / InterleaveShader ::ShaderDataBuffer), SH/Common/{interleave,deinterleave}.frag:4-8 */
+typedef struct lgcu_interleave_data { int32_t gridSize[4]; int32_t viewportSize[4]; } lgcu_interleave_data;
+/* DebugRenderer.h:84-87 (DebugRendererShader::QuadData), SH/Common/debugRenderer.vert:9-12: (min.x, min.y, max.x, max.y) in [0,1] screen units */
+typedef struct lgcu_debug_quad_data { float minmax[4]; } lgcu_debug_quad_data;
 #pragma pack(pop)
 
 /* Per-pixel fragment attributes: the CUDA-side form of what the rasteriser hands to
@@ -141,8 +145,9 @@ int lgcu_direct_light(const lgcu_direct_lighting_data *params, const lgcu_image 
                       const lgcu_image *directLight, const lgcu_rows *rows, void *stream);
 
 /* K3 "MipBuilderPass" (one level): SH/Common/mipLevelBuilder.frag:17-43, driver MipBuilder.h:142-181.
- * src and dst are single-level views (level l-1 and l). filterType >= 0.5 (Depth) has no live caller and
- * returns LGCU_ERR_UNSUPPORTED. */
+ * src and dst are single-level views (level l-1 and l). filterType < 0.5 = Avg (:23-28, the live path);
+ * filterType >= 0.5 = Depth (:29-42; MipBuilder::FilterTypes::Depth, MipBuilder.h:136-141, 168): per 2x2 block
+ * (min of .x, max of .y, sum((y - x) * z) / (max - min) / 4, 0). */
 int lgcu_mip_level(const lgcu_mip_level_builder_data *params, const lgcu_image *srcLevel, const lgcu_image *dstLevel,
                    const lgcu_rows *rows, void *stream);
 
@@ -227,6 +232,31 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
                               const lgcu_image *denoised, const lgcu_image *directLight,
                               const lgcu_image *blurredDirectLight, const lgcu_image *albedo,
                               const lgcu_image *swapchain, const lgcu_rows *rows, void *stream);
+
+/* ---- the passes either side of the hot path ---------------------------------------------------------
+ * Interleaved rendering (InterleaveBuilder.h:14-80): a gridSize.x x gridSize.y pattern of pixels is regrouped into gridSize
+ * contiguous sub-images of size viewportSize / gridSize (integer division) and back. Both are pure index permutations of
+ * texels (bit-exact); source and destination must have the same format (RGBA16F, RG32F or RGBA32F) and the same size =
+ * viewportSize, with viewportSize >= gridSize >= 1 per axis. rows = destination rows.
+ *   lgcu_deinterleave: SH/Common/deinterleave.frag:17-29  dst(p) = src(InterleavePixel(p)),
+ *                      InterleavePixel(p) = (p % (viewport / grid)) * grid + p / (viewport / grid)
+ *   lgcu_interleave:   SH/Common/interleave.frag:16-28    dst(p) = src(DeinterleavePixel(p)),
+ *                      DeinterleavePixel(p) = (p % grid) * (viewport / grid) + p / grid
+ * (The reference's InterleaveBuilder::Interleave binds the de-interleave program by mistake, InterleaveBuilder.h:60-65; this
+ * entry point is the shipped interleave.frag.spv, i.e. what the builder means to run.) */
+int lgcu_deinterleave(const lgcu_interleave_data *params, const lgcu_image *interleaved, const lgcu_image *deinterleaved,
+                      const lgcu_rows *rows, void *stream);
+int lgcu_interleave(const lgcu_interleave_data *params, const lgcu_image *deinterleaved, const lgcu_image *interleaved,
+                    const lgcu_rows *rows, void *stream);
+
+/* "DebugInfoPass" (DebugRenderer.h:13-63, SH/Common/debugRenderer.vert:15-24, debugRenderer.frag:11-15): one textured quad
+ * covering [minmax.xy, minmax.zw] of the target (screen units), loadOp eLoad, opaque: every target pixel whose centre lies in
+ * the quad receives texture(src, t), t = (pixel centre / target size - min) / (max - min), sampled with the pass's sampler
+ * (clamp-to-edge, linear min/mag, nearest mip; single-level source views as on the live path, SSVGIRenderer.h:344-350) and
+ * written with the target's format conversion (B8G8R8A8_SRGB swapchain, or RGBA16F / RGBA32F). Pixels outside the quad keep
+ * their contents. The renderer issues one call per debug view (tile layout DebugRenderer.h:27-57). rows = target rows. */
+int lgcu_debug_overlay(const lgcu_debug_quad_data *params, const lgcu_image *src, const lgcu_image *target, const lgcu_rows *rows,
+                       void *stream);
 
 /* ---- rasterisation front end: "ShadowPass" and the raster half of "GBufferPass"  --------------------
  * The reference draws every scene object with drawIndexed through the fixed-function rasteriser (SSVGIRenderer.h:63-104 shadow

@@ -49,6 +49,9 @@ int lgh_upload_light_depth(lgh_renderer *r, const float *hostDepth, uint32_t siz
 int lgh_upload_mesh(lgh_renderer *r, const lgcu_vertex *hostVertices, uint32_t nVertices, const uint32_t *hostIndices, uint32_t nIndices,
                     const lgcu_draw *hostDraws, uint32_t nDraws, const lgcu_draw_call_data *hostObjects, uint32_t nObjects);
 int lgh_use_mesh(lgh_renderer *r, uint32_t enable);
+/* DebugRenderer::RenderImageViews over the finished frame (SSVGIRenderer.h:344-350): off by default — the reference always draws
+ * it, the parity tests and the bench look at the frame before it. Takes effect with the next lgh_render_frame / lgh_capture_frame. */
+int lgh_set_debug_overlay(lgh_renderer *r, uint32_t enable);
 
 /* One frame: SSVGIRenderer::RenderFrame + RenderGraph::Execute. rows may be NULL (whole frame; required for pass-granular).
  * profile != 0 records per-pass GPU events (read them with lgh_get_profile after lgh_sync). */

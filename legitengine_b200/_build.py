@@ -32,6 +32,7 @@ CUDA_UNITS = {
     "k_gather_fast.cu": [],
     "k_p2p.cu": [],
     "k_raster.cu": ["-fmad=false"],
+    "k_aux.cu": ["-fmad=false"],
     "lgcu_api.cu": ["-fmad=false"],
 }
 

@@ -82,6 +82,8 @@ BlurLayerBuilderData = _packed("BlurLayerBuilderData", [("size", C.c_int32 * 4),
 IndirectLightingData = _packed("IndirectLightingData", [("viewMatrix", LgcuMat4), ("projMatrix", LgcuMat4), ("viewportExtent", C.c_float * 4)])
 DenoiserData = _packed("DenoiserData", [("viewMatrix", LgcuMat4), ("projMatrix", LgcuMat4), ("viewportExtent", C.c_float * 4), ("radius", C.c_int32)])
 FinalGathererData = _packed("FinalGathererData", [("viewMatrix", LgcuMat4), ("projMatrix", LgcuMat4)])
+InterleaveData = _packed("InterleaveData", [("gridSize", C.c_int32 * 4), ("viewportSize", C.c_int32 * 4)])
+DebugQuadData = _packed("DebugQuadData", [("minmax", C.c_float * 4)])
 
 
 class RowCopy(C.Structure):
@@ -141,6 +143,10 @@ PASS_SIGNATURES = {
     "gi_gather": [P(IndirectLightingData), IMG, IMG, IMG, IMG, IMG, C.c_uint32, ROWS],
     "denoise": [P(DenoiserData), IMG, IMG, IMG, IMG, ROWS],
     "final_gather": [P(FinalGathererData), IMG, IMG, IMG, IMG, IMG, ROWS],
+    # interleaved rendering and the debug overlay
+    "deinterleave": [P(InterleaveData), IMG, IMG, ROWS],
+    "interleave": [P(InterleaveData), IMG, IMG, ROWS],
+    "debug_overlay": [P(DebugQuadData), IMG, IMG, ROWS],
 }
 FUSED_SIGNATURES = {
     "gbuffer_direct_light": [P(GBufferBuilderData), P(DirectLightingData), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, P(ClearValues), IMG, IMG, IMG, IMG, IMG, IMG, IMG, ROWS],

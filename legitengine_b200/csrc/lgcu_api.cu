@@ -328,11 +328,11 @@ int lgcu_mip_level(const lgcu_mip_level_builder_data *params, const lgcu_image *
                    void *stream) {
   int st = LGCU_OK;
   if (!params || !srcLevel || !dstLevel) return fail(LGCU_ERR_INVALID_ARGUMENT, "mip_level: null argument");
-  if (!(params->filterType < 0.5f)) return fail(LGCU_ERR_UNSUPPORTED, "mip_level: Depth filter (filterType >= 0.5) has no live caller in the reference");
   if (!chainFormat(srcLevel->format) || srcLevel->format != dstLevel->format)
     return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "mip_level: formats %u -> %u", srcLevel->format, dstLevel->format);
   MipLevelArgs a;
   a.format = srcLevel->format;
+  a.depthFilter = params->filterType < 0.5f ? 0 : 1; // mipLevelBuilder.frag:22
   if (!resolveLevel(srcLevel, 0, "mip src", &a.src, &st) || !resolveLevel(dstLevel, 0, "mip dst", &a.dst, &st)) return st;
   if (a.dst.w * 2 > a.src.w || a.dst.h * 2 > a.src.h)
     return fail(LGCU_ERR_INVALID_ARGUMENT, "mip_level: dst %dx%d is not a half-size level of src %dx%d", a.dst.w, a.dst.h, a.src.w, a.src.h);
@@ -357,6 +357,77 @@ int lgcu_blur_level(const lgcu_blur_layer_builder_data *params, const lgcu_image
     return fail(LGCU_ERR_INVALID_ARGUMENT, "blur_level: radius %d / size %dx%d on a %dx%d level", a.radius, a.sizeX, a.sizeY, a.src.w, a.src.h);
   a.rows = rowRange(rows, dstLevel->baseMip, a.dst.h);
   return cudaStatus(launchBlurLevel(a, static_cast<cudaStream_t>(stream)), "blur_level");
+}
+
+// ---- interleaved rendering and the debug overlay ---------------------------------------------------
+static int fillInterleaveArgs(const char *what, const lgcu_interleave_data *params, const lgcu_image *interleaved, const lgcu_image *deinterleaved,
+                              const lgcu_image *dst, const lgcu_rows *rows, InterleaveArgs *a) {
+  int st = LGCU_OK;
+  if (!params || !interleaved || !deinterleaved) return fail(LGCU_ERR_INVALID_ARGUMENT, "%s: null argument", what);
+  const uint32_t f = interleaved->format;
+  if (f != deinterleaved->format || (f != LGCU_FORMAT_R16G16B16A16_SFLOAT && f != LGCU_FORMAT_R32G32_SFLOAT && f != LGCU_FORMAT_R32G32B32A32_SFLOAT))
+    return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "%s: formats %u / %u (one of RGBA16F, RG32F, RGBA32F on both sides)", what, interleaved->format, deinterleaved->format);
+  if (!resolveLevel(interleaved, 0, "interleaved", &a->interleaved, &st) || !resolveLevel(deinterleaved, 0, "deinterleaved", &a->deinterleaved, &st)) return st;
+  if (!sameSize(a->interleaved, a->deinterleaved, "interleaved", "deinterleaved", &st)) return st;
+  const int w = a->interleaved.w, h = a->interleaved.h;
+  if (params->viewportSize[0] != w || params->viewportSize[1] != h || params->gridSize[0] < 1 || params->gridSize[1] < 1 || params->gridSize[0] > w ||
+      params->gridSize[1] > h)
+    return fail(LGCU_ERR_INVALID_ARGUMENT, "%s: viewportSize %dx%d / gridSize %dx%d on %dx%d images", what, params->viewportSize[0], params->viewportSize[1],
+                params->gridSize[0], params->gridSize[1], w, h);
+  a->texelBytes = (int)texelSize(f);
+  a->gridX = params->gridSize[0];
+  a->gridY = params->gridSize[1];
+  a->cellsX = w / a->gridX; // deinterleave.frag:19, interleave.frag:18
+  a->cellsY = h / a->gridY;
+  a->rows = rowRange(rows, dst->baseMip, h);
+  return LGCU_OK;
+}
+
+int lgcu_deinterleave(const lgcu_interleave_data *params, const lgcu_image *interleaved, const lgcu_image *deinterleaved, const lgcu_rows *rows, void *stream) {
+  InterleaveArgs a;
+  const int st = fillInterleaveArgs("deinterleave", params, interleaved, deinterleaved, deinterleaved, rows, &a);
+  if (st != LGCU_OK) return st;
+  return cudaStatus(launchDeinterleave(a, static_cast<cudaStream_t>(stream)), "deinterleave");
+}
+
+int lgcu_interleave(const lgcu_interleave_data *params, const lgcu_image *deinterleaved, const lgcu_image *interleaved, const lgcu_rows *rows, void *stream) {
+  InterleaveArgs a;
+  const int st = fillInterleaveArgs("interleave", params, interleaved, deinterleaved, interleaved, rows, &a);
+  if (st != LGCU_OK) return st;
+  return cudaStatus(launchInterleave(a, static_cast<cudaStream_t>(stream)), "interleave");
+}
+
+int lgcu_debug_overlay(const lgcu_debug_quad_data *params, const lgcu_image *src, const lgcu_image *target, const lgcu_rows *rows, void *stream) {
+  int st = LGCU_OK;
+  if (!params || !src || !target) return fail(LGCU_ERR_INVALID_ARGUMENT, "debug_overlay: null argument");
+  if (src->format != LGCU_FORMAT_R16G16B16A16_SFLOAT && src->format != LGCU_FORMAT_R32G32_SFLOAT && src->format != LGCU_FORMAT_R32G32B32A32_SFLOAT)
+    return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "debug_overlay: source format %u", src->format);
+  if (target->format != LGCU_FORMAT_B8G8R8A8_SRGB && target->format != LGCU_FORMAT_R16G16B16A16_SFLOAT && target->format != LGCU_FORMAT_R32G32B32A32_SFLOAT)
+    return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "debug_overlay: target format %u", target->format);
+  if (src->mipCount != 1) return fail(LGCU_ERR_UNSUPPORTED, "debug_overlay: %u-level source view (the live path shows single-level views, SSVGIRenderer.h:344-350)", src->mipCount);
+  DebugOverlayArgs a;
+  a.srcFormat = src->format;
+  a.targetFormat = target->format;
+  if (!resolveLevel(src, 0, "debug src", &a.src, &st) || !resolveLevel(target, 0, "debug target", &a.target, &st)) return st;
+  const float *mm = params->minmax;
+  const float w = (float)a.target.w, h = (float)a.target.h;
+  // debugRenderer.vert:20 for corners (0,0) and (1,1), then the viewport transform (this unit is compiled with -fmad=false)
+  const float ndcX0 = (mm[0] + 0.0f * (mm[2] - mm[0])) * 2.0f - 1.0f, ndcX1 = (mm[0] + 1.0f * (mm[2] - mm[0])) * 2.0f - 1.0f;
+  const float ndcY0 = (mm[1] + 0.0f * (mm[3] - mm[1])) * 2.0f - 1.0f, ndcY1 = (mm[1] + 1.0f * (mm[3] - mm[1])) * 2.0f - 1.0f;
+  a.wx0 = (ndcX0 + 1.0f) * (w / 2.0f);
+  a.wx1 = (ndcX1 + 1.0f) * (w / 2.0f);
+  a.wy0 = (ndcY0 + 1.0f) * (h / 2.0f);
+  a.wy1 = (ndcY1 + 1.0f) * (h / 2.0f);
+  if (!(a.wx1 > a.wx0) || !(a.wy1 > a.wy0)) return LGCU_OK; // degenerate or non-finite quad covers nothing
+  const RowRange rr = rowRange(rows, 0, a.target.h);
+  auto lo = [](float v, int limit) { return v <= 0.0f ? 0 : (v >= (float)limit ? limit : (int)v); };
+  a.x0 = lo(a.wx0 - 1.0f, a.target.w);
+  a.x1 = lo(a.wx1 + 1.0f, a.target.w);
+  a.y0 = lo(a.wy0 - 1.0f, a.target.h);
+  a.y1 = lo(a.wy1 + 1.0f, a.target.h);
+  if (a.y0 < rr.y0) a.y0 = rr.y0;
+  if (a.y1 > rr.y1) a.y1 = rr.y1;
+  return cudaStatus(launchDebugOverlay(a, static_cast<cudaStream_t>(stream)), "debug_overlay");
 }
 
 int lgcu_mip_blur_chain(const lgcu_image *chain, const lgcu_image *blurred, int32_t radius, const lgcu_rows *rows, void *stream) {

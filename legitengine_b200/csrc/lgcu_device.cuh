@@ -114,6 +114,21 @@ __device__ __forceinline__ float glmMin(float a, float b) { return (b < a) ? b :
 __device__ __forceinline__ float glmMax(float a, float b) { return (a < b) ? b : a; }
 __device__ __forceinline__ float saturatef(float x) { return glmMin(glmMax(x, 0.0f), 1.0f); }
 
+// ---- render-target conversion to B8G8R8A8_SRGB (LV/Swapchain.h:108): clamp, sRGB OETF on RGB, linear alpha, RTN to 8 bit
+__device__ __forceinline__ uint32_t unorm8(float x) {
+  if (!(x > 0.0f)) return 0u;
+  if (x > 1.0f) x = 1.0f;
+  return (uint32_t)(x * 255.0f + 0.5f);
+}
+__device__ __forceinline__ float linearToSrgb(float c) {
+  if (!(c > 0.0f)) c = 0.0f;
+  if (c > 1.0f) c = 1.0f;
+  return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ uint32_t packBgra8Srgb(float4 v) {
+  return unorm8(linearToSrgb(v.z)) | (unorm8(linearToSrgb(v.y)) << 8) | (unorm8(linearToSrgb(v.x)) << 16) | (unorm8(saturatef(v.w)) << 24);
+}
+
 // ---- exact-order bilinear / trilinear (strict kernels; compile the TU with -fmad=false) ---------------------------
 // lerp(p, q, t) = p + (q - p) * t; bilinear = lerp(lerp(t00, t10, a), lerp(t01, t11, a), b).
 struct BilinearTaps {

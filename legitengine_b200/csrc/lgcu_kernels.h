@@ -34,6 +34,7 @@ struct DirectLightArgs {
 
 struct MipLevelArgs {
   uint32_t format;
+  int depthFilter; // MipLevelBuilderData.filterType >= 0.5 (MipBuilder::FilterTypes::Depth)
   LevelView src, dst;
   RowRange rows; // in dst rows
 };
@@ -134,6 +135,24 @@ struct RasterArgs { // ShadowPass / raster half of GBufferPass (k_raster.cu)
 };
 uint64_t rasterScratchBytes(uint32_t nTriangles, uint32_t width, uint32_t height);
 cudaError_t launchRaster(const RasterArgs &a, int smCount, cudaStream_t s);
+
+struct InterleaveArgs { // (de)interleave passes: a texel permutation between two images of one format and size
+  int texelBytes;           // 8 or 16
+  int gridX, gridY;         // gridSize
+  int cellsX, cellsY;       // viewportSize / gridSize (integer division): size of one de-interleaved sub-image
+  LevelView interleaved, deinterleaved;
+  RowRange rows;            // destination rows
+};
+cudaError_t launchDeinterleave(const InterleaveArgs &a, cudaStream_t s); // deinterleaved <- interleaved
+cudaError_t launchInterleave(const InterleaveArgs &a, cudaStream_t s);   // interleaved <- deinterleaved
+
+struct DebugOverlayArgs { // one quad of DebugInfoPass
+  uint32_t srcFormat, targetFormat;
+  float wx0, wy0, wx1, wy1; // window-space rectangle of the quad ("rule D")
+  int x0, x1, y0, y1;       // conservative pixel box of the rectangle, clipped to the target and to the rows
+  LevelView src, target;
+};
+cudaError_t launchDebugOverlay(const DebugOverlayArgs &a, cudaStream_t s);
 
 constexpr int kMaxCopies = 64, kMaxFlags = 32;
 struct RowCopyArgs { // contiguous slabs (16-byte multiples), any of them possibly in a peer GPU's memory

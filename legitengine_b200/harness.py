@@ -42,6 +42,7 @@ def load_harness() -> C.CDLL:
         lib.lgh_upload_light_depth.argtypes = [R, C.c_void_p, C.c_uint32]
         lib.lgh_upload_mesh.argtypes = [R, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         lib.lgh_use_mesh.argtypes = [R, C.c_uint32]
+        lib.lgh_set_debug_overlay.argtypes = [R, C.c_uint32]
         lib.lgh_render_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         lib.lgh_render_stages.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         H64 = C.c_ubyte * 64
@@ -117,6 +118,10 @@ class Renderer:
         memory): frames then start from the mesh (ShadowPass + GBufferRasterPass rasterise it on the device). Asynchronous."""
         _check(self.lib.lgh_upload_mesh(self.handle, C.c_void_p(mesh.vertices.ctypes.data), len(mesh.vertices), C.c_void_p(mesh.indices.ctypes.data), len(mesh.indices),
                                         C.c_void_p(mesh.draws.ctypes.data), len(mesh.draws), C.c_void_p(mesh.objects.ctypes.data), len(mesh.objects)), "lgh_upload_mesh")
+
+    def set_debug_overlay(self, enable: bool) -> None:
+        """DebugInfoPass (thumbnails of normal / albedo / indirectLight / denoisedIndirectLight) over the finished frame."""
+        _check(self.lib.lgh_set_debug_overlay(self.handle, 1 if enable else 0), "lgh_set_debug_overlay")
 
     def use_mesh(self, enable: bool) -> None:
         _check(self.lib.lgh_use_mesh(self.handle, 1 if enable else 0), "lgh_use_mesh")

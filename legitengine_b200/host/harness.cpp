@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/lgcu_harness.h"
+#include "legit_cuda/InterleaveBuilder.h"
 #include "legit_cuda/SSVGIRenderer.h"
 
 using namespace legit_cuda;
@@ -47,6 +48,7 @@ struct lgh_renderer {
   std::unique_ptr<Buffer> meshVertices, meshIndices, meshDraws, meshObjects, rasterScratch;
   lgcu_mesh_scene meshDesc{};
   bool useMesh = false;
+  bool debugOverlay = false;
 
   std::unique_ptr<ImageData> swapchainImage;
   std::unique_ptr<ImageView> swapchainView;
@@ -93,6 +95,7 @@ struct lgh_renderer {
     options.denoiserRadius = denoiserRadius;
     options.giFlags = giFlags;
     options.stages = stages;
+    options.debugOverlay = debugOverlay;
     if (rows) {
       options.useRows = true;
       options.rows = *rows;
@@ -256,6 +259,12 @@ int lgh_upload_mesh(lgh_renderer *r, const lgcu_vertex *hostVertices, uint32_t n
     r->meshDesc.nTriangles = uint32_t(triangles);
     r->useMesh = true;
   })
+}
+
+int lgh_set_debug_overlay(lgh_renderer *r, uint32_t enable) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_set_debug_overlay: null renderer");
+  r->debugOverlay = enable != 0;
+  return LGCU_OK;
 }
 
 int lgh_use_mesh(lgh_renderer *r, uint32_t enable) {

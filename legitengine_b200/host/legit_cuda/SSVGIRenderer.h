@@ -17,13 +17,15 @@
 //  * FrameOptions::mode == Fused replaces groups of passes by the fused entry points (frame front = K1+K2+level-0 blur+mips 1..4,
 //    frame chains = remaining blur/mip work, packed GI gather, K6+K7): identical images, 6 launches instead of 46 passes.
 //    PassGranular is the 1:1 pass list (47 passes incl. shadow).
-//  * The debug overlay (DebugRenderer, :344-350) is out of scope.
+//  * The debug overlay (DebugRenderer, :344-350) is drawn when FrameOptions::debugOverlay is set (the reference always draws it; the
+//    parity tests and the bench compare the frame before it).
 #pragma once
 
 #include <memory>
 
 #include "BlurBuilder.h"
 #include "Camera.h"
+#include "DebugRenderer.h"
 #include "MipBuilder.h"
 
 namespace legit_cuda {
@@ -77,12 +79,13 @@ struct FrameOptions {
   // Multi-GPU strips run the fused frame in stages with a halo exchange between them; a single GPU runs all.
   enum Stage : uint32_t { StageFront = 1, StageChains = 2, StageGather = 4, StageFinal = 8, StageAll = 15 };
   uint32_t stages = StageAll;
+  bool debugOverlay = false; // DebugInfoPass: thumbnails of normal / albedo / indirectLight / denoisedIndirectLight over the frame (:344-350)
 };
 
 class SSVGIRenderer {
 public:
   explicit SSVGIRenderer(Core *_core)
-      : mipBuilder(_core), blurBuilder(_core), screenspaceSampler(SamplerAddressMode::eClampToEdge, Filter::eLinear, SamplerMipmapMode::eLinear),
+      : mipBuilder(_core), blurBuilder(_core), debugRenderer(_core), screenspaceSampler(SamplerAddressMode::eClampToEdge, Filter::eLinear, SamplerMipmapMode::eLinear),
         shadowmapSampler(SamplerAddressMode::eClampToEdge, Filter::eLinear, SamplerMipmapMode::eNearest, true), core(_core) {}
 
   void RecreateSceneResources(Scene *) {}
@@ -477,11 +480,21 @@ public:
                                      "DenoiseGatheringPass");
                          }));
     }
+
+    if (options.debugOverlay && (options.mode == FrameOptions::Mode::PassGranular || (stages & FrameOptions::StageFinal))) {
+      std::vector<RenderGraph::ImageViewProxyId> debugProxies; // :344-350
+      debugProxies.push_back(res->normal.imageViewProxy->Id());
+      debugProxies.push_back(res->albedo.imageViewProxy->Id());
+      debugProxies.push_back(res->indirectLight.imageViewProxy->Id());
+      debugProxies.push_back(res->denoisedIndirectLight.imageViewProxy->Id());
+      debugRenderer.RenderImageViews(graph, frameInfo.memoryPool, frameInfo.swapchainImageViewProxyId, debugProxies, useRows ? &options.rows : nullptr);
+    }
   }
 
   void ReloadShaders() {
     mipBuilder.ReloadShaders();
     blurBuilder.ReloadShaders();
+    debugRenderer.ReloadShaders();
   }
 
   // :391-419
@@ -521,6 +534,7 @@ private:
   vk::Extent2D viewportExtent;
   MipBuilder mipBuilder;
   BlurBuilder blurBuilder;
+  DebugRenderer debugRenderer;
   Sampler screenspaceSampler;
   Sampler shadowmapSampler;
   Core *core;

@@ -229,32 +229,50 @@ class P2PStripRenderer(StripRenderer):
         if lst[1]:
             abi.check(self._lgcu.lgcu_copy_rows(lst[0], lst[1], self._stream), "lgcu_copy_rows")
 
-    def render(self, gi_flags: int = abi.GI_DEFAULT) -> None:
+    STAGE_MARKS = ("start", "front", "chain_halo", "chains", "gather_halo", "gather_final", "present")
+
+    def render(self, gi_flags: int = abi.GI_DEFAULT, marks=None) -> None:
+        """One frame. `marks` (optional): a list that receives one torch.cuda.Event per STAGE_MARKS entry, recorded on the current
+        stream after that stage was enqueued (un-captured frames only) — the per-rank, per-stage profile of bench.py --shard strips."""
         if not self._ready:
             self._setup()
         r, rows = self.renderer, self.rows
         have = rows[1] > rows[0]
+
+        def mark():
+            if marks is not None:
+                ev = self._torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+
         abi.check(self._lgcu.lgcu_frame_counter_bump(self._counter, self._stream), "lgcu_frame_counter_bump")
         self._signal(self._sig_free)
         self._wait(self._wait_ack, lag=1)
+        mark()
         if have:
             r.render_stages(harness.STAGE_FRONT, rows, gi_flags=gi_flags)
+        mark()
         self._signal(self._sig_front)
         self._wait(self._wait_front)
         self._copy(self._pull_chains)
+        mark()
         if have:
             r.render_stages(harness.STAGE_CHAINS, rows, gi_flags=gi_flags)
+        mark()
         self._signal(self._sig_chains)
         self._wait(self._wait_chains)
         self._copy(self._pull_gather)
         self._signal(self._sig_ack)
+        mark()
         if have:
             r.render_stages(harness.STAGE_GATHER | harness.STAGE_FINAL, rows, gi_flags=gi_flags)
+        mark()
         if self._is_pusher:
             self._wait(self._wait_free)
             self._copy(self._push)
             self._signal(self._sig_delivered)
         self._wait(self._wait_delivered)
+        mark()
 
     def capture(self, gi_flags: int = abi.GI_DEFAULT) -> None:
         torch = self._torch

@@ -313,6 +313,85 @@ extern "C" int ref_shadowmap_vertex_stage(const lgcu_draw_call_data *drawCall, c
 }
 #endif
 
+#if REF_PASS == 10 || REF_PASS == 11
+// Interleaved rendering: 10 = spirv/Common/deinterleave.frag.spv (InterleaveBuilder::Deinterleave, InterleaveBuilder.h:14-45),
+// 11 = spirv/Common/interleave.frag.spv (what InterleaveBuilder::Interleave means to run, :47-80). Set 0: binding 0 = the UBO
+// (gridSize, viewportSize), binding 1 = the source image; render area = the view's size (:16, :49).
+#if REF_PASS == 10
+extern "C" int ref_deinterleave(const lgcu_interleave_data *params, const lgcu_image *srcImg, const lgcu_image *dstImg, const lgcu_rows *rows) {
+#else
+extern "C" int ref_interleave(const lgcu_interleave_data *params, const lgcu_image *srcImg, const lgcu_image *dstImg, const lgcu_rows *rows) {
+#endif
+  int w, h, sw, sh, y0, y1;
+  orc_level_size(dstImg, 0, &w, &h);
+  orc_level_size(srcImg, 0, &sw, &sh);
+  // same argument contract as include/lgcu.h (keeps every texelFetch of the module in bounds)
+  if (sw != w || sh != h || srcImg->format != dstImg->format || params->viewportSize[0] != w || params->viewportSize[1] != h || params->gridSize[0] < 1 ||
+      params->gridSize[1] < 1 || params->gridSize[0] > w || params->gridSize[1] > h)
+    return LGCU_ERR_INVALID_ARGUMENT;
+  ref_row_range(rows, 0, h, &y0, &y1);
+#pragma omp parallel
+  {
+    RefShaderInstance s;
+    RefSampler2D sSrc(srcImg);
+    glm::vec4 out;
+    s.resource(0, 0, (void *)params);
+    s.resource(0, 1, &sSrc);
+    s.bindScreenCoord(0);
+    s.output(0, &out, sizeof(out));
+#pragma omp for schedule(dynamic, 8)
+    for (int y = y0; y < y1; y++)
+      for (int x = 0; x < w; x++) {
+        s.setPixel(x, y, w, h);
+        s.invoke();
+        ref_store(dstImg, x, y, out);
+      }
+  }
+  return LGCU_OK;
+}
+#endif
+
+#if REF_PASS == 12
+// One quad of DebugInfoPass: fragment stage = spirv/Common/debugRenderer.frag.spv (set 1 binding 0 = srcSampler, location 0 =
+// fragTexCoord; DebugRenderer.h:44-50). The vendored C++ backend has no gl_VertexIndex builtin, so the 4-vertex stage
+// (debugRenderer.vert:15-24) and the rasterisation of the axis-aligned quad are restated ("rule D", see oracle/ssvgi_oracle.c).
+extern "C" int ref_debug_overlay(const lgcu_debug_quad_data *params, const lgcu_image *srcImg, const lgcu_image *targetImg, const lgcu_rows *rows) {
+  int w, h, y0, y1;
+  orc_level_size(targetImg, 0, &w, &h);
+  ref_row_range(rows, 0, h, &y0, &y1);
+  const glm::vec4 minmax(params->minmax[0], params->minmax[1], params->minmax[2], params->minmax[3]);
+  const glm::vec2 p0 = (glm::vec2(minmax.x, minmax.y) + glm::vec2(0.0f, 0.0f) * (glm::vec2(minmax.z, minmax.w) - glm::vec2(minmax.x, minmax.y))) * 2.0f - glm::vec2(1.0f);
+  const glm::vec2 p1 = (glm::vec2(minmax.x, minmax.y) + glm::vec2(1.0f, 1.0f) * (glm::vec2(minmax.z, minmax.w) - glm::vec2(minmax.x, minmax.y))) * 2.0f - glm::vec2(1.0f);
+  const float wx0 = (p0.x + 1.0f) * (float(w) / 2.0f), wx1 = (p1.x + 1.0f) * (float(w) / 2.0f);
+  const float wy0 = (p0.y + 1.0f) * (float(h) / 2.0f), wy1 = (p1.y + 1.0f) * (float(h) / 2.0f);
+  if (!(wx1 > wx0) || !(wy1 > wy0)) return LGCU_OK;
+#pragma omp parallel
+  {
+    RefShaderInstance s;
+    RefSampler2D sSrc(srcImg);
+    glm::vec2 texCoord;
+    glm::vec4 out;
+    s.resource(1, 0, &sSrc);
+    s.input(0, &texCoord, sizeof(texCoord));
+    s.output(0, &out, sizeof(out));
+#pragma omp for schedule(dynamic, 8)
+    for (int y = y0; y < y1; y++) {
+      const float cy = float(y) + 0.5f;
+      if (!(wy0 <= cy && cy < wy1)) continue;
+      for (int x = 0; x < w; x++) {
+        const float cx = float(x) + 0.5f;
+        if (!(wx0 <= cx && cx < wx1)) continue;
+        texCoord = glm::vec2((cx - wx0) / (wx1 - wx0), (cy - wy0) / (wy1 - wy0));
+        s.setPixel(x, y, w, h);
+        s.invoke();
+        ref_store(targetImg, x, y, out);
+      }
+    }
+  }
+  return LGCU_OK;
+}
+#endif
+
 #if REF_PASS == 1
 extern "C" int ref_num_threads(void) { return omp_get_max_threads(); }
 extern "C" void ref_set_num_threads(int n) { omp_set_num_threads(n); }

@@ -34,6 +34,10 @@ int orc_final_gather(const lgcu_final_gatherer_data *params, const lgcu_image *d
                      const lgcu_image *blurredDirectLight, const lgcu_image *albedo, const lgcu_image *indirectLight,
                      const lgcu_image *swapchain, const lgcu_rows *rows);
 
+int orc_deinterleave(const lgcu_interleave_data *params, const lgcu_image *interleaved, const lgcu_image *deinterleaved, const lgcu_rows *rows);
+int orc_interleave(const lgcu_interleave_data *params, const lgcu_image *deinterleaved, const lgcu_image *interleaved, const lgcu_rows *rows);
+int orc_debug_overlay(const lgcu_debug_quad_data *params, const lgcu_image *src, const lgcu_image *target, const lgcu_rows *rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,8 +85,12 @@ def test_invalid_calls_are_rejected_without_a_device():
     assert lib.lgcu_mip_level(C.byref(mp), None, None, None, None) == abi.LGCU_ERR_INVALID_ARGUMENT
     assert lib.lgcu_mip_level(C.byref(mp), C.byref(img), C.byref(img), None, None) == abi.LGCU_ERR_INVALID_ARGUMENT  # null base
     assert b"null image" in lib.lgcu_last_error()
-    depth_filter = abi.MipLevelBuilderData(1.0)
-    assert lib.lgcu_mip_level(C.byref(depth_filter), C.byref(img), C.byref(img), None, None) == abi.LGCU_ERR_UNSUPPORTED
+    depth_filter = abi.MipLevelBuilderData(1.0)  # FilterTypes::Depth is implemented: the same argument checks apply
+    assert lib.lgcu_mip_level(C.byref(depth_filter), C.byref(img), C.byref(img), None, None) == abi.LGCU_ERR_INVALID_ARGUMENT
+    ip = abi.InterleaveData((C.c_int32 * 4)(4, 4, 0, 0), (C.c_int32 * 4)(64, 64, 0, 0))
+    assert lib.lgcu_deinterleave(C.byref(ip), C.byref(img), C.byref(img), None, None) == abi.LGCU_ERR_INVALID_ARGUMENT  # null base
+    assert lib.lgcu_interleave(None, None, None, None, None) == abi.LGCU_ERR_INVALID_ARGUMENT
+    assert lib.lgcu_debug_overlay(None, None, None, None, None) == abi.LGCU_ERR_INVALID_ARGUMENT
     d32 = abi.LgcuImage()
     lib.lgcu_image_layout(C.byref(d32), abi.FORMAT_D32_SFLOAT, 64, 64, 1)
     assert lib.lgcu_mip_level(C.byref(mp), C.byref(d32), C.byref(d32), None, None) == abi.LGCU_ERR_UNSUPPORTED_FORMAT

@@ -157,3 +157,33 @@ def test_frame_from_mesh_scene(mode, camera):
         assert [n for n, _ in r.profile()][1] == "FrameFrontPass"
         assert np.array_equal(r.download_image("swapchain").level_raw(0), a.astype(np.uint8))
     r.close()
+
+
+@pytest.mark.parametrize("mode", [harness.MODE_PASS_GRANULAR, harness.MODE_FUSED])
+def test_debug_overlay_on_the_frame(mode):
+    """DebugInfoPass (SSVGIRenderer.h:344-350 -> DebugRenderer::RenderImageViews): four thumbnails over the finished frame, against
+    the oracle's frame + the oracle's overlay pass; the rest of the frame is untouched."""
+    from tests import aux_helpers as A
+    from oracle import loader
+
+    W, Hh = 640, 360
+    sc, p, ref = H.oracle_frame(11, W, Hh)
+    want = images.HostImage(abi.FORMAT_B8G8R8A8_SRGB, W, Hh, 1)
+    want.level_bytes(0)[...] = ref.swapchain.level_bytes(0)
+    for quad, name in zip(A.debug_tiles(4), ("normal", "albedo", "indirectLight", "denoisedIndirectLight")):
+        assert loader.port().debug_overlay(C.byref(quad), C.byref(getattr(ref, name).view()), C.byref(want.view()), None) == 0
+    r = harness.Renderer(W, Hh)
+    r.upload_scene(sc)
+    r.render_frame(mode, 0, abi.GI_DEFAULT)
+    r.sync()
+    plain = r.download_image("swapchain").level_raw(0).astype(np.int32)
+    r.set_debug_overlay(True)
+    r.render_frame(mode, 0, abi.GI_DEFAULT, profile=True)
+    r.sync()
+    assert [n for n, _ in r.profile()][-1] == "DebugInfoPass"
+    got = r.download_image("swapchain").level_raw(0).astype(np.int32)
+    assert (np.abs(got - want.level_raw(0).astype(np.int32)) > 1).mean() < 1e-3
+    changed = (got != plain).any(axis=2)
+    ys, xs = np.nonzero(changed)
+    assert changed.any() and ys.max() <= int(0.12 * Hh) + 1 and xs.max() <= int(0.48 * W) + 1 and ys.min() >= int(0.02 * Hh) - 1 and xs.min() >= int(0.02 * W) - 1
+    r.close()
