@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-present", action="store_true", help="strips: skip the composite of the swapchain strips on rank 0")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="strips: p2p = our copy/flag kernels over NVLink peer memory (CUDA IPC); nccl = torch.distributed send/recv per slab")
+    ap.add_argument("--balance", type=int, default=3, help="strips (p2p): up to this many measure -> rebalance rounds of the strip boundaries (0 = equal rows)")
     ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -416,25 +417,59 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     W, H = workload_size(args.workload)
     m = scene.frame_matrices(W, H)
     seed = 0xC0FFEE
-    bounds = sharding.strip_bounds(H, world)
-    y0, y1 = bounds[rank]
-    # every rank generates (and keeps in pinned memory) only its own strip of the rasterised scene
-    frag_host = torch.empty((max(y1 - y0, 1), W * 32), dtype=torch.uint8).pin_memory()
-    frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
-    full_view_ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
-    scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
     objects = scene.scene_objects(seed)
     shadow = torch.from_numpy(scene.scene_shadow_map(seed, m)).pin_memory()
     swap_host = torch.empty((H, W * 4), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.Stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        cls = multigpu.P2PStripRenderer if args.transport == "p2p" else multigpu.StripRenderer
-        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present)
+    cls = multigpu.P2PStripRenderer if args.transport == "p2p" else multigpu.StripRenderer
+    gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
+
+    def build(bounds):
+        """Strip renderer for `bounds` with this rank's strip of the rasterised scene generated into pinned memory and uploaded."""
+        y0, y1 = bounds[rank]
+        frag_host = torch.empty((max(y1 - y0, 1), W * 32), dtype=torch.uint8).pin_memory()
+        frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
+        scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
+        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present, bounds=bounds)
         sr.renderer.upload_objects(objects.ctypes.data, len(objects))
         sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
-        sr.upload_strip(full_view_ptr, W * 32)
-        gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
+        ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
+        sr.upload_strip(ptr, W * 32)
+        return sr, frag_host, ptr
+
+    def stage_profile(sr, frames=8):
+        """Per-rank GPU time between the stage marks of un-captured frames, all-gathered: {stage: [ms of rank 0, 1, ...]}."""
+        n_marks = len(sr.STAGE_MARKS)
+        acc = torch.zeros(n_marks - 1, device="cuda")
+        for i in range(frames + 2):
+            marks = []
+            sr.render(gi_flags, marks=marks)
+            torch.cuda.synchronize()
+            if i >= 2:
+                acc += torch.tensor([marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks - 1)], device="cuda") / frames
+        dist.barrier()
+        every = [torch.zeros_like(acc) for _ in range(world)]
+        dist.all_gather(every, acc)
+        return {name: [round(float(e[j]), 4) for e in every] for j, name in enumerate(sr.STAGE_MARKS[1:])}
+
+    bounds = sharding.strip_bounds(H, world)
+    balance_log = []
+    with torch.cuda.stream(stream):
+        sr, frag_host, full_view_ptr = build(bounds)
+        # cost-aware strips (sharding.rebalance_bounds): measure every rank's own kernel time, move the boundaries, rebuild
+        for _ in range(args.balance if args.transport == "p2p" else 0):
+            prof = stage_profile(sr, frames=4)
+            own = [prof["front"][r] + prof["chains"][r] + prof["gather_final"][r] for r in range(world)]
+            new_bounds = sharding.rebalance_bounds(bounds, own, H)
+            balance_log.append({"bounds": bounds, "own_ms": [round(v, 4) for v in own]})
+            if new_bounds == bounds:
+                break
+            torch.cuda.synchronize()
+            sr.close()
+            del frag_host
+            bounds = new_bounds
+            sr, frag_host, full_view_ptr = build(bounds)
 
         def barrier():
             dist.barrier()
@@ -477,20 +512,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         recv_all = torch.tensor([received], device="cuda", dtype=torch.int64)
         dist.all_reduce(recv_all)
         # per-rank, per-stage GPU time of un-captured frames (events between the stages on every rank): shows where a strip waits
-        stage_ms = None
-        if args.transport == "p2p":
-            n_marks, prof_frames = len(sr.STAGE_MARKS), 8
-            acc = torch.zeros(n_marks - 1, device="cuda")
-            for i in range(prof_frames + 2):
-                marks = []
-                sr.render(gi_flags, marks=marks)
-                torch.cuda.synchronize()
-                if i >= 2:
-                    acc += torch.tensor([marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks - 1)], device="cuda") / prof_frames
-            dist.barrier()
-            every = [torch.zeros_like(acc) for _ in range(world)]
-            dist.all_gather(every, acc)
-            stage_ms = {name: [round(float(e[j]), 4) for e in every] for j, name in enumerate(sr.STAGE_MARKS[1:])}
+        stage_ms = stage_profile(sr) if args.transport == "p2p" else None
     if rank == 0:
         npx = W * H
         peak, peak_src = measured_peak_gbs()
@@ -509,9 +531,10 @@ def run_strips(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "e2e": {"value": npx / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": 5 * args.steps * world,
-            "kernels_per_frame": 5,
+            "gpu_launches": 6 * args.steps * world,
+            "kernels_per_frame": 6,
             "stage_ms_per_rank": stage_ms,
+            "balance": balance_log,
             "roofline_frame": {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
                                "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes": frame_bytes,
                                "note": "whole frame over all GPUs, pass-granular algorithmic bytes; peak = N x measured single-GPU HBM copy bandwidth"},

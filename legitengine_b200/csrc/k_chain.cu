@@ -15,6 +15,7 @@ cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s) {
   for (int l = 1; l < a.levels; l++) {
     MipLevelArgs m;
     m.format = a.format;
+    m.depthFilter = 0; // BuildMips(..., FilterTypes::Avg) on the live path (SSVGIRenderer.h:207-208)
     m.src = a.chain.lv[l - 1];
     m.dst = a.chain.lv[l];
     m.rows = levelRows(l, m.dst.h);
@@ -41,21 +42,26 @@ cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------------
 // frameChainsKernel — what remains of K3 + K4 after the frame-front kernel (k_front.cu), in ONE launch:
 //   grid part : blurLayerBuilder (radius 2, SH/Common/blurLayerBuilder.frag:17-35) of levels 1..gridLevels of both chains;
-//   tail part : one CTA per chain builds mip levels gridLevels+1..9 (mipLevelBuilder.frag:17-28) and blurs them. These
-//               levels hold < 2 % of the texels; walking them in one CTA replaces 20 launch-latency-bound launches.
+//   tail part : one thread-block CLUSTER of 8 CTAs per chain (chainTailKernel) builds mip levels gridLevels+1..9
+//               (mipLevelBuilder.frag:17-28) and blurs them. Level l+1 needs all of level l, so the levels are walked one after
+//               the other with a hardware cluster barrier (release / acquire at cluster scope) in between. These levels hold
+//               < 2 % of the texels; the cluster replaces 20 launch-latency-bound launches, and its 2048 threads keep this
+//               serial chain off the critical path of a multi-GPU strip, where it costs as much as on a whole frame.
 // Blur: a thread produces four vertically adjacent output texels of one column from a 4 x 7 register window (28 loads
 // instead of 64), each output summed in the shader's order (x outer, y inner, sequential fp32) so the result is bit-exact.
+#include <cooperative_groups.h>
+
 namespace lgcu {
 namespace {
 
 constexpr uint32_t kF16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, kRG32 = LGCU_FORMAT_R32G32_SFLOAT;
 constexpr int kBlurTileW = 32, kBlurTileH = 32, kChainThreads = 256, kBlurRowsPerThread = 4;
+constexpr int kTailCluster = 8; // CTAs per chain in the tail cluster (portable cluster size limit)
 
 struct ChainsLaunch {
   ChainsArgs a;
   int blockBegin[2][kFrontMipLevels + 1]; // first CTA of (chain, level - 1); [..][gridLevels] = end
   int rowBegin[kFrontMipLevels], rowEnd[kFrontMipLevels];
-  int tailBlocks; // 0 or 2
 };
 
 template <bool kCoherent> __device__ __forceinline__ uint2 loadTexel(const LevelView &l, int x, int y) {
@@ -111,34 +117,37 @@ template <uint32_t F> __device__ __forceinline__ void mipTexel(const LevelView &
   Texel<F>::store(dst, x, y, sum);
 }
 
-template <uint32_t F> __device__ void chainTail(const ChainsArgs &a, const PyramidView &chain, const PyramidView &blurred) {
-  // mip levels one after the other (each reads the level just written by this CTA), then their blurs
+template <uint32_t F> __device__ void chainTail(const ChainsArgs &a, const PyramidView &chain, const PyramidView &blurred, int ctaRank) {
+  namespace cg = cooperative_groups;
+  const int first = ctaRank * kChainThreads + threadIdx.x, stride = kTailCluster * kChainThreads;
+  // mip levels one after the other (each reads the level the cluster has just written: __ldcg, i.e. from L2), then their blurs
   for (int l = a.gridLevels + 1; l < a.levels; l++) {
     const LevelView &src = chain.lv[l - 1], &dst = chain.lv[l];
-    for (int i = threadIdx.x; i < dst.w * dst.h; i += kChainThreads) mipTexel<F>(src, dst, i % dst.w, i / dst.w);
-    __syncthreads();
+    for (int i = first; i < dst.w * dst.h; i += stride) mipTexel<F>(src, dst, i % dst.w, i / dst.w);
+    cg::this_cluster().sync();
   }
   for (int l = a.gridLevels + 1; l < a.levels; l++) {
     const LevelView &src = chain.lv[l], &dst = blurred.lv[l];
     const int groups = (src.h + kBlurRowsPerThread - 1) / kBlurRowsPerThread;
-    for (int i = threadIdx.x; i < src.w * groups; i += kChainThreads) {
+    for (int i = first; i < src.w * groups; i += stride) {
       const int x = i % src.w, y = (i / src.w) * kBlurRowsPerThread;
       blurColumnR<F, true>(a.radius, src, dst, x, y, min(kBlurRowsPerThread, src.h - y));
     }
   }
 }
 
+// grid = 2 clusters of kTailCluster CTAs: cluster 0 walks the directLight chain, cluster 1 the depthMoments chain
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kChainThreads) chainTailKernel(const __grid_constant__ ChainsArgs a) {
+  const int chain = blockIdx.x / kTailCluster, ctaRank = blockIdx.x % kTailCluster;
+  if (chain == 0)
+    chainTail<kF16>(a, a.light, a.blurredLight, ctaRank);
+  else
+    chainTail<kRG32>(a, a.moments, a.blurredMoments, ctaRank);
+}
+
 __global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_constant__ ChainsLaunch p) {
   const ChainsArgs &a = p.a;
   int b = blockIdx.x;
-  if (b < p.tailBlocks) {
-    if (b == 0)
-      chainTail<kF16>(a, a.light, a.blurredLight);
-    else
-      chainTail<kRG32>(a, a.moments, a.blurredMoments);
-    return;
-  }
-  b -= p.tailBlocks;
   const int chain = b >= p.blockBegin[1][0] ? 1 : 0;
   int l = 1;
   while (l < a.gridLevels && b >= p.blockBegin[chain][l]) l++; // level l occupies [blockBegin[l-1], blockBegin[l])
@@ -174,9 +183,9 @@ cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s) {
     p.blockBegin[chain][a.gridLevels] = blocks;
   }
   if (a.gridLevels == 0) p.blockBegin[1][0] = 0x7fffffff;
-  p.tailBlocks = a.levels > a.gridLevels + 1 ? 2 : 0;
-  if (blocks + p.tailBlocks == 0) return cudaSuccess;
-  frameChainsKernel<<<blocks + p.tailBlocks, kChainThreads, 0, s>>>(p);
+  // the tail first: it is a dependent chain of small levels on 16 SMs, the blur grid then fills the other SMs behind it
+  if (a.levels > a.gridLevels + 1) chainTailKernel<<<2 * kTailCluster, kChainThreads, 0, s>>>(a);
+  if (blocks > 0) frameChainsKernel<<<blocks, kChainThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -178,14 +178,16 @@ __device__ __forceinline__ PendingSample issueSample(const StepRow &st, const Di
 }
 __device__ __forceinline__ float bilerpQuad(const float4 &q, const Footprint &f) { return lerpf(lerpf(q.x, q.y, f.a), lerpf(q.z, q.w, f.a), f.b); }
 
-template <bool kQuads, bool kSmem, int kMinBlocks, bool kPipe = false>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
+// kT = threads per CTA: a CTA shades a 64 x (kT / 4) pixel tile (256 -> 64x64, 128 -> 64x32). The smaller tile doubles the CTA count
+// for row strips and small frames, where the grid would otherwise be a couple of waves with a long tail (multi-GPU strips).
+template <bool kQuads, bool kSmem, int kMinBlocks, bool kPipe = false, int kT = kThreads>
+__global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
                                                                           const float4 *__restrict__ quads) {
   __shared__ StepRow sRows[kSmem ? kMaxSteps : 1];
   __shared__ DirEntry sDir[kSmem ? kGatherDirs : 1];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
-  const int tileX = blockIdx.x * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * kTile;
+  const int tileX = blockIdx.x * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
   const float vpx = a.viewport[0], vpy = a.viewport[1];
   const float invVpx = 1.0f / vpx, invVpy = 1.0f / vpy;
   const V3 cam = v3(a.cam[0], a.cam[1], a.cam[2]);
@@ -194,15 +196,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) gatherFastKernel(const _
   const uint2 *__restrict__ light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
   const int tx = 4 * (t & 15), ty = 4 * (t >> 4);
 
+  // gridDim.z splits the 16 pattern classes over CTAs (1, 2, 4, 8 or 16 slices): finer work units for grids of a few waves
+  const int idxPerCta = 16 / (int)gridDim.z, idx0 = (int)blockIdx.z * idxPerCta;
 #pragma unroll 1
-  for (int idx = 0; idx < 16; idx++) { // one pattern class per pass (CTA-uniform)
+  for (int idx = idx0; idx < idx0 + idxPerCta; idx++) { // one pattern class per pass (CTA-uniform)
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
     if (kSmem) { // this pass's table rows -> shared memory: the march then reads them with vector loads instead of LDCU + MOV
       __syncthreads();
       constexpr int kRowWords = kMaxSteps * (int)(sizeof(StepRow) / 4), kDirWords = kGatherDirs * (int)(sizeof(DirEntry) / 4);
       const uint32_t *srcRows = reinterpret_cast<const uint32_t *>(&tb.row[idx * kMaxSteps]), *srcDir = reinterpret_cast<const uint32_t *>(&tb.dir[idx][0]);
-      for (int i = t; i < kRowWords; i += kThreads) reinterpret_cast<uint32_t *>(sRows)[i] = srcRows[i];
+      for (int i = t; i < kRowWords; i += kT) reinterpret_cast<uint32_t *>(sRows)[i] = srcRows[i];
       if (t < kDirWords) reinterpret_cast<uint32_t *>(sDir)[t] = srcDir[t];
       __syncthreads();
     } else if (!__any_sync(0xffffffffu, active)) {
@@ -513,29 +517,34 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   if (a.rows.y1 <= a.rows.y0) return cudaSuccess;
   FastTables f;
   if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, &f, nullptr)) return launchGatherStrict(a, t, s);
-  const dim3 grid((a.indirect.w + kTile - 1) / kTile, (a.rows.y1 - (a.rows.y0 & ~3) + kTile - 1) / kTile);
+  const int rowsSpan = a.rows.y1 - (a.rows.y0 & ~3);
+  const dim3 grid((a.indirect.w + kTile - 1) / kTile, (rowsSpan + kTile - 1) / kTile);
   static const int variant = getenv("LGCU_GATHER_VARIANT") ? atoi(getenv("LGCU_GATHER_VARIANT")) : 0; // development switch
-  const float4 *q = static_cast<const float4 *>(scratch);
+  static const int smCount = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const float4 *quadsPtr = static_cast<const float4 *>(scratch);
+  // fewer than ~6 waves of 64x64 tiles (4 CTAs per SM): use 64x32 tiles so that the tail of the last wave is half as long
+  const bool smallTiles = variant == 9 || (variant == 0 && (long long)grid.x * grid.y < 6LL * 4 * smCount); // variant 10 forces 64x64
+  // 4 slices of 4 pattern classes per tile: 4x more, 4x shorter work units (measured r01h: -5 % on a 4K frame, -14 % on an 8K strip of
+  // 544 rows; 16 slices lose the L1 reuse between the passes of a tile and are slower on whole frames)
+  static const int slices = getenv("LGCU_GATHER_SLICES") ? atoi(getenv("LGCU_GATHER_SLICES")) : 4; // development switch: 1, 2, 4, 8, 16
   if (!scratch)
     gatherFastKernel<false, false, 4><<<grid, kThreads, 0, s>>>(a, f, nullptr);
   else if (variant == 1)
-    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, q);
+    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
   else if (variant == 2)
-    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, q);
-  else if (variant == 3)
-    gatherFastKernel<true, true, 3><<<grid, kThreads, 0, s>>>(a, f, q);
+    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
   else if (variant == 4)
-    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, q);
-  else if (variant == 5)
-    gatherFastKernel<true, false, 4, true><<<grid, kThreads, 0, s>>>(a, f, q);
-  else if (variant == 6)
-    gatherFastKernel<true, true, 3, true><<<grid, kThreads, 0, s>>>(a, f, q);
+    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
   else if (variant == 7)
-    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, q);
-  else if (variant == 8)
-    gatherFastKernel<true, true, 2, true><<<grid, kThreads, 0, s>>>(a, f, q);
+    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
+  else if (smallTiles)
+    gatherFastKernel<true, false, 8, false, 128><<<dim3(grid.x, (rowsSpan + 31) / 32, slices), 128, 0, s>>>(a, f, quadsPtr);
   else
-    gatherFastKernel<true, false, 4><<<grid, kThreads, 0, s>>>(a, f, q);
+    gatherFastKernel<true, false, 4><<<dim3(grid.x, grid.y, slices), kThreads, 0, s>>>(a, f, quadsPtr);
   return cudaGetLastError();
 }
 

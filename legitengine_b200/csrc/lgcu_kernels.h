@@ -34,7 +34,7 @@ struct DirectLightArgs {
 
 struct MipLevelArgs {
   uint32_t format;
-  int depthFilter; // MipLevelBuilderData.filterType >= 0.5 (MipBuilder::FilterTypes::Depth)
+  int depthFilter = 0; // MipLevelBuilderData.filterType >= 0.5 (MipBuilder::FilterTypes::Depth)
   LevelView src, dst;
   RowRange rows; // in dst rows
 };

@@ -54,11 +54,14 @@ class StripRenderer:
 
     EXCHANGED = sharding.CHAINS + sharding.BLURRED + ("swapchain",)
 
-    def __init__(self, width: int, height: int, rank: int, world: int, dist, stream: int = 0, root: int = 0, present: bool = True):
+    def __init__(self, width: int, height: int, rank: int, world: int, dist, stream: int = 0, root: int = 0, present: bool = True, bounds=None):
         import torch
 
         self.width, self.height, self.rank, self.world, self.dist, self.root, self.present = width, height, rank, world, dist, root, present
-        self.bounds = sharding.strip_bounds(height, world)
+        # equal-row strips unless the caller supplies cost-aware ones (sharding.rebalance_bounds)
+        self.bounds = list(bounds) if bounds is not None else sharding.strip_bounds(height, world)
+        if len(self.bounds) != world or any(y0 % sharding.GRANULE for y0, _ in self.bounds):
+            raise ValueError("StripRenderer: one strip per rank, starting on multiples of %d rows" % sharding.GRANULE)
         self.rows = self.bounds[rank]
         self.renderer = harness.Renderer(width, height, stream=stream)
         self.plan_chains = sharding.plan_chains(self.bounds, width, height)

@@ -58,6 +58,44 @@ def strip_bounds(height: int, world: int, granule: int = GRANULE) -> List[Tuple[
     return bounds
 
 
+def rebalance_bounds(bounds: Sequence[Tuple[int, int]], costs: Sequence[float], height: int, granule: int = GRANULE) -> List[Tuple[int, int]]:
+    """Cost-aware strip boundaries. `costs[r]` is the time rank r spent on its own strip `bounds[r]` (its kernels only, not the
+    time it waited for halos). The GI gather's cost per row depends on what the rows show (≈ ±25 % between strips of the synthetic
+    8K scene), so equal row counts leave the slowest strip on the critical path of every frame. The measured cost is spread
+    evenly over the rows of each strip (piecewise-constant cost density), and the new boundaries cut the cumulative cost into
+    `world` equal parts, snapped to multiples of `granule` rows; every rank keeps at least one granule. Deterministic: all ranks
+    compute the same bounds from the same all-gathered costs. Iterate (measure -> rebalance) two or three times to converge."""
+    world = len(bounds)
+    if world != len(costs) or world < 1:
+        raise ValueError("rebalance_bounds: one cost per strip")
+    blocks = (height + granule - 1) // granule
+    if world == 1 or blocks <= world or not all(c > 0.0 for (y0, y1), c in zip(bounds, costs) if y1 > y0):
+        return list(bounds)
+    # cost of every granule block under the piecewise-constant density
+    block_cost = [0.0] * blocks
+    for (y0, y1), c in zip(bounds, costs):
+        if y1 <= y0:
+            continue
+        per_row = c / (y1 - y0)
+        for b in range(y0 // granule, (y1 + granule - 1) // granule):
+            lo, hi = max(b * granule, y0), min((b + 1) * granule, y1, height)
+            if hi > lo:
+                block_cost[b] += per_row * (hi - lo)
+    total = sum(block_cost)
+    cuts, acc, b = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while b < blocks and acc + block_cost[b] * 0.5 < target:  # nearest block boundary to the target
+            acc += block_cost[b]
+            b += 1
+        cut = min(max(b, cuts[-1] + 1), blocks - (world - r))  # at least one block per rank, and room for the ranks after it
+        cuts.append(cut)
+        if cut != b:  # re-sync the accumulator with the boundary actually chosen
+            acc, b = sum(block_cost[:cut]), cut
+    cuts.append(blocks)
+    return [(min(cuts[r] * granule, height), min(cuts[r + 1] * granule, height)) for r in range(world)]
+
+
 def level_height(height: int, level: int) -> int:
     return height >> level
 

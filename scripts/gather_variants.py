@@ -13,6 +13,7 @@ import torch  # noqa: E402
 from legitengine_b200 import abi, harness, scene  # noqa: E402
 
 W, H = (3840, 2160) if len(sys.argv) < 3 else (int(sys.argv[1]), int(sys.argv[2]))
+ROWS = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) >= 5 else None  # time the gather stage on a row strip only
 m = scene.frame_matrices(W, H)
 frags = scene.scene_fragments(0xC0FFEE, W, H, m)
 objects = scene.scene_objects(0xC0FFEE)
@@ -26,9 +27,28 @@ for _ in range(3):
     r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
 r.sync()
 acc, n = {}, 10
-for _ in range(n):
-    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT, profile=True)
+if ROWS is None:
+    for _ in range(n):
+        r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT, profile=True)
+        r.sync()
+        for name, ms in r.profile():
+            acc[name] = acc.get(name, 0.0) + ms / n
+else:
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.Stream()
+    r.close()
+    r = harness.Renderer(W, H, stream=stream.cuda_stream)
+    r.upload_fragments(frags.ctypes.data, frags.strides[0])
+    r.upload_objects(objects.ctypes.data, len(objects))
+    r.upload_light_depth(shadow.ctypes.data, 1024)
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
     r.sync()
-    for name, ms in r.profile():
-        acc[name] = acc.get(name, 0.0) + ms / n
-print(json.dumps({"variant": os.environ.get("LGCU_GATHER_VARIANT", "0"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
+    with torch.cuda.stream(stream):
+        for i in range(n + 3):
+            if i == 3:
+                ev0.record(stream)
+            r.render_stages(harness.STAGE_GATHER, rows=ROWS)
+        ev1.record(stream)
+    r.sync()
+    acc["GatherStage(rows %d..%d)" % ROWS] = ev0.elapsed_time(ev1) / n
+print(json.dumps({"variant": os.environ.get("LGCU_GATHER_VARIANT", "0"), "slices": os.environ.get("LGCU_GATHER_SLICES", "1"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))

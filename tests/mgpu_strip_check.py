@@ -19,6 +19,7 @@ def main():
 
     W, H = int(sys.argv[1]), int(sys.argv[2])
     transport = sys.argv[3] if len(sys.argv) > 3 else "nccl"
+    uneven = len(sys.argv) > 4 and sys.argv[4] == "uneven"  # cost-aware (non-uniform) strip boundaries
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -30,7 +31,13 @@ def main():
         whole.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
         whole.sync()
         cls = multigpu.P2PStripRenderer if transport == "p2p" else multigpu.StripRenderer
-        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream)
+        bounds = None
+        if uneven:  # what sharding.rebalance_bounds produces for a frame whose lower strips are the expensive ones
+            from legitengine_b200 import sharding
+
+            bounds = sharding.rebalance_bounds(sharding.strip_bounds(H, world), [1.0 + 0.6 * r for r in range(world)], H)
+            assert bounds != sharding.strip_bounds(H, world)
+        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, bounds=bounds)
         # only this rank's strip of the fragments is uploaded: the rest of the fragment buffer stays unwritten
         sr.renderer.upload_objects(sc.objects.ctypes.data, len(sc.objects))
         sr.renderer.upload_light_depth(np.ascontiguousarray(sc.shadow_map).ctypes.data, sc.shadow_map.shape[0])

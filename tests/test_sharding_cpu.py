@@ -150,3 +150,32 @@ def test_strip_pipeline_gloo(world, size, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), W, Hh, str(tmp_path)), nprocs=world, join=True)
     for rank in range(world):
         assert (tmp_path / f"rank{rank}.txt").read_text() == "ok"
+
+
+def test_rebalance_bounds_equalises_measured_cost():
+    """Cost-aware strips: contiguous cover, granule-aligned, at least one granule each, and the predicted max cost drops to
+    within one granule's worth of the mean."""
+    H, world = 4320, 8
+    b = sharding.strip_bounds(H, world)
+    costs = [0.885, 1.003, 1.061, 1.098, 1.103, 0.903, 0.810, 0.713]  # profiles/r01f: gather+final ms per rank, 8K on 8 GPUs
+    nb = sharding.rebalance_bounds(b, costs, H)
+    assert nb[0][0] == 0 and nb[-1][1] == H and all(nb[i][1] == nb[i + 1][0] for i in range(world - 1))
+    assert all(y0 % sharding.GRANULE == 0 and y1 > y0 for y0, y1 in nb)
+
+    def predicted(bounds):
+        dens = np.zeros(H)
+        for (y0, y1), c in zip(b, costs):
+            dens[y0:y1] = c / (y1 - y0)
+        return [dens[y0:y1].sum() for y0, y1 in bounds]
+
+    before, after = predicted(b), predicted(nb)
+    mean = sum(costs) / world
+    assert abs(sum(after) - sum(costs)) < 1e-9
+    assert max(after) < max(before) and max(after) <= mean + 1.5 * sharding.GRANULE * max(costs) / 528
+    # fixed points and degenerate inputs
+    assert sharding.rebalance_bounds(b, [1.0] * world, H) == b
+    assert sharding.rebalance_bounds([(0, H)], [3.0], H) == [(0, H)]
+    tiny = sharding.strip_bounds(48, 8)  # 3 granules for 8 ranks: left alone
+    assert sharding.rebalance_bounds(tiny, [1.0] * 8, 48) == tiny
+    skew = sharding.rebalance_bounds(sharding.strip_bounds(256, 4), [100.0, 1.0, 1.0, 1.0], 256)
+    assert all(y1 - y0 >= sharding.GRANULE for y0, y1 in skew) and skew[0][1] < 64
