@@ -84,6 +84,12 @@ int lgh_last_pass_count(lgh_renderer *r);
 int lgh_image_desc(lgh_renderer *r, const char *name, lgcu_image *out);
 int lgh_download_image(lgh_renderer *r, const char *name, uint32_t level, void *host, uint64_t hostPitchBytes, uint32_t rowBegin, uint32_t rowEnd);
 
+/* InterleaveBuilder on the rendergraph (src/Render/Common/InterleaveBuilder.h:14-80): Deinterleave(image -> a) then Interleave(a -> b)
+ * on two transient images of the source's format and size; both results are copied to host memory (tightly packed rows of
+ * hostPitchBytes) and the call waits for them. `srcName` is a single-level image of the last frame (see lgh_image_desc). */
+int lgh_run_interleave(lgh_renderer *r, const char *srcName, uint32_t gridX, uint32_t gridY, void *hostDeinterleaved, void *hostRoundTrip,
+                       uint64_t hostPitchBytes);
+
 int lgh_sync(lgh_renderer *r);
 
 /* Per-pass GPU times of the last profiled frame: names are written '\n'-separated into nameBuf, durations (ms) into ms.

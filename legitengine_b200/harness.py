@@ -58,6 +58,7 @@ def load_harness() -> C.CDLL:
         lib.lgh_last_pass_count.argtypes = [R]
         lib.lgh_image_desc.argtypes = [R, C.c_char_p, abi.IMG]
         lib.lgh_download_image.argtypes = [R, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
+        lib.lgh_run_interleave.argtypes = [R, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.lgh_sync.argtypes = [R]
         lib.lgh_get_profile.argtypes = [R, C.c_char_p, C.c_uint64, C.POINTER(C.c_float), C.c_uint32]
         lib.lgh_allocated_bytes.argtypes = [R]
@@ -173,6 +174,16 @@ class Renderer:
     def download_swapchain(self, host_ptr: int, pitch: int, rows=None) -> None:
         y0, y1 = rows if rows is not None else (0, self.height)
         _check(self.lib.lgh_download_image(self.handle, b"swapchain", 0, C.c_void_p(host_ptr), pitch, y0, y1), "lgh_download_image")
+
+    def run_interleave(self, name: str, grid=(4, 4)):
+        """InterleaveBuilder::Deinterleave then ::Interleave of image `name` through the rendergraph: (de-interleaved, round trip) as
+        raw (h, w, texel bytes) uint8 arrays."""
+        d = self.image_desc(name)
+        ts = abi.TEXEL_SIZE[d.format]
+        a = np.zeros((d.height, d.width, ts), dtype=np.uint8)
+        b = np.zeros_like(a)
+        _check(self.lib.lgh_run_interleave(self.handle, name.encode(), grid[0], grid[1], C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), d.width * ts), "lgh_run_interleave")
+        return a, b
 
     def download_image(self, name: str) -> images.HostImage:
         """Whole image (all levels) into a HostImage with the canonical layout; synchronises."""

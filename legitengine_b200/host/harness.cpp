@@ -267,6 +267,43 @@ int lgh_set_debug_overlay(lgh_renderer *r, uint32_t enable) {
   return LGCU_OK;
 }
 
+int lgh_run_interleave(lgh_renderer *r, const char *srcName, uint32_t gridX, uint32_t gridY, void *hostDeinterleaved, void *hostRoundTrip, uint64_t hostPitchBytes) {
+  if (!r || !srcName || !hostDeinterleaved || !hostRoundTrip) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_run_interleave: null argument");
+  ImageView *src = r->findImage(srcName);
+  if (!src || src->GetDesc()->mipCount != 1) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_run_interleave: '%s' is not a resolved single-level image", srcName);
+  try {
+    // InterleaveBuilder on the rendergraph, as the reference's interleaved renderers use it (LSGIRenderer.h:83-85): two transient
+    // images of the source's format and size, Deinterleave(src -> a), Interleave(a -> b), then both are read back
+    RenderGraph *graph = r->core->GetRenderGraph();
+    InterleaveBuilder builder(r->core.get());
+    const lgcu_image *d = src->GetDesc();
+    const glm::uvec2 size(d->width, d->height);
+    auto srcProxy = graph->AddExternalImageView(src);
+    auto imgA = graph->AddImage(vk::Format(d->format), 1, 1, size, colorImageUsage);
+    auto imgB = graph->AddImage(vk::Format(d->format), 1, 1, size, colorImageUsage);
+    auto viewA = graph->AddImageView(imgA->Id(), 0, 1, 0, 1);
+    auto viewB = graph->AddImageView(imgB->Id(), 0, 1, 0, 1);
+    r->memoryPool.MapBuffer();
+    builder.Deinterleave(graph, &r->memoryPool, srcProxy->Id(), viewA->Id(), glm::uvec2(gridX, gridY));
+    builder.Interleave(graph, &r->memoryPool, viewA->Id(), viewB->Id(), glm::uvec2(gridX, gridY));
+    graph->Execute(r->stream, nullptr, nullptr);
+    const uint64_t rowBytes = uint64_t(d->width) * lgcu_format_texel_size(d->format);
+    if (hostPitchBytes < rowBytes) throw std::runtime_error("lgh_run_interleave: host pitch");
+    void *hosts[2] = {hostDeinterleaved, hostRoundTrip};
+    ImageView *views[2] = {graph->GetResolvedImageView(viewA->Id()), graph->GetResolvedImageView(viewB->Id())};
+    for (int i = 0; i < 2; i++) {
+      const lgcu_image *v = views[i]->GetDesc();
+      CudaCheck(cudaMemcpy2DAsync(hosts[i], hostPitchBytes, static_cast<const uint8_t *>(v->base) + v->levelOffset[0], v->levelPitch[0], rowBytes, d->height,
+                                  cudaMemcpyDeviceToHost, r->stream),
+                "download interleave result");
+    }
+    CudaCheck(cudaStreamSynchronize(r->stream), "cudaStreamSynchronize");
+    return LGCU_OK;
+  } catch (const std::exception &e) {
+    return setError(LGCU_ERR_CUDA, "lgh_run_interleave: %s", e.what());
+  }
+}
+
 int lgh_use_mesh(lgh_renderer *r, uint32_t enable) {
   if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_use_mesh: null renderer");
   if (enable && !r->meshVertices) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_use_mesh: no mesh uploaded");

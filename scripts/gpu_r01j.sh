@@ -1,0 +1,15 @@
+#!/bin/bash
+# r01j: final verification of the round: all GPU tests, smoke(), default bench line, ncu launch list, full capture of the gather and of the raster kernels.
+TAG=${1:-r01j}
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
+tail -4 $OUT/pytest_gpu_$TAG.log
+timeout 300 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -2 $OUT/smoke_$TAG.log
+timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
+cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_launch_$TAG.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gatherFast|rasterBig|rasterResolveFragments|frameFront" -s 8 -c 4 -f -o $OUT/frame_$TAG \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_full_$TAG.log 2>&1
+tail -2 $OUT/ncu_full_$TAG.log | cut -c1-200
+ls -la $OUT/frame_$TAG.ncu-rep

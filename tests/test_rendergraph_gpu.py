@@ -187,3 +187,26 @@ def test_debug_overlay_on_the_frame(mode):
     ys, xs = np.nonzero(changed)
     assert changed.any() and ys.max() <= int(0.12 * Hh) + 1 and xs.max() <= int(0.48 * W) + 1 and ys.min() >= int(0.02 * Hh) - 1 and xs.min() >= int(0.02 * W) - 1
     r.close()
+
+
+@pytest.mark.parametrize("grid", [(4, 4), (3, 2)])
+def test_interleave_builder_on_the_rendergraph(grid):
+    """legit_cuda::InterleaveBuilder (mirror of src/Render/Common/InterleaveBuilder.h) through RenderGraph::AddPass with transient
+    images: Deinterleave moves exactly the texels deinterleave.frag names, and Interleave brings a divisible viewport back."""
+    W, Hh = 640, 360
+    sc, p, ref = H.oracle_frame(11, W, Hh)
+    r = harness.Renderer(W, Hh)
+    r.upload_scene(sc)
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
+    r.sync()
+    src = r.download_image("indirectLight").level_bytes(0)
+    de, back = r.run_interleave("indirectLight", grid)
+    gx, gy = grid
+    x, y = np.meshgrid(np.arange(W), np.arange(Hh))
+    dvx, dvy = W // gx, Hh // gy
+    assert np.array_equal(de, src[(y % dvy) * gy + y // dvy, (x % dvx) * gx + x // dvx])
+    want_back = de[(y % gy) * dvy + y // gy, (x % gx) * dvx + x // gx]  # interleave.frag applied to the de-interleaved image
+    assert np.array_equal(back, want_back)
+    if W % gx == 0 and Hh % gy == 0:
+        assert np.array_equal(back, src)
+    r.close()
