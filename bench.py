@@ -38,9 +38,10 @@ BYTES_PER_PX = {"resolve": 68.0, "light": 36.0, "mips": 26.67, "blur": 42.67, "g
 FRAME_BYTES_PER_PX = 258.67
 SHADOW_MAP_BYTES = 4 * 1024 * 1024
 METRIC = "full_gi_frame_mpix_per_s"
-# warp-level instructions one launch of the GI gather executes on the 4K synthetic frame (ncu smsp__inst_executed.sum of the bench's
-# own frame, profiles/r01j_gather_full.md): the algorithmic work of the kernel that is bound by instruction issue, not by HBM
-GATHER_WARP_INST_4K = 1.290e9
+# warp-level instructions one launch of the GI gather executes on the 4K synthetic frame, and the DRAM bytes it moves (ncu
+# smsp__inst_executed.sum, dram__bytes_read.sum + dram__bytes_write.sum of this scene's frame: profiles/r01l_gather_traffic_xslices.csv)
+GATHER_WARP_INST_4K = 1.314e9
+GATHER_DRAM_TRAFFIC_4K = 347067904 + 59241984
 SM_COUNT, ISSUE_PER_SM_PER_CLK = 148, 4  # 4 warp schedulers per SM, one warp instruction per scheduler per clock
 
 
@@ -265,6 +266,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms_per_step = ms_total / args.steps
     value = world * npx / (ms_per_step * 1e-3) / 1e6
 
+    # per-frame distribution of the same replayed frame (median and p10 / p90), one event pair per frame
+    dist_frames = 100
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(dist_frames)]
+    with torch.cuda.stream(stream):
+        for e0, e1 in pairs:
+            e0.record(stream)
+            r.replay_frame()
+            e1.record(stream)
+    torch.cuda.synchronize()
+    per_frame = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)
+    frame_ms = {"median": per_frame[dist_frames // 2], "p10": per_frame[dist_frames // 10], "p90": per_frame[(dist_frames * 9) // 10], "frames": dist_frames}
+
     # --- e2e: host fragments in, swapchain out, every step. Like the reference's InFlightQueue (LV/PresentQueue.h:62: one command
     # buffer per in-flight frame) several frames are in flight: each slot owns a renderer (image set + captured graph), a stream and
     # a pinned swapchain buffer, so the H2D copy of frame i+1 and the D2H copy of frame i-1 overlap the kernels of frame i.
@@ -357,7 +370,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         frame_bytes = FRAME_BYTES_PER_PX * npx + SHADOW_MAP_BYTES
         roofline = {
             "kernel": "gi_gather (IndirectLightPass)", "bound": "hbm", "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
-            "peak": peak, "unit": "GB/s", "frac": (gather_bytes / (gather_ms * 1e-3) / 1e9 / peak) if gather_ms else None, "traffic": None,
+            "peak": peak, "unit": "GB/s", "frac": (gather_bytes / (gather_ms * 1e-3) / 1e9 / peak) if gather_ms else None,
+            "traffic": GATHER_DRAM_TRAFFIC_4K if (W, H) == (3840, 2160) and not args.strict else None, "algorithmic_bytes": gather_bytes,
             "peak_source": peak_src, "ms": gather_ms,
             "note": "the gather is FP32-ALU/L1 bound, not HBM bound (SURVEY.md F7): achieved = 41.33 B/px compulsory bytes / its measured time",
         }
@@ -399,6 +413,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline": roofline,
             "roofline_issue": roofline_issue,
             "roofline_frame": roofline_frame,
+            "frame_ms": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in frame_ms.items()},
             "pass_ms": {k: round(v, 4) for k, v in pass_ms.items()},
             "pass_ms_mesh": {k: round(v, 4) for k, v in pass_ms_mesh.items()},
         }

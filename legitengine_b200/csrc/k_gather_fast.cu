@@ -182,12 +182,16 @@ __device__ __forceinline__ float bilerpQuad(const float4 &q, const Footprint &f)
 // for row strips and small frames, where the grid would otherwise be a couple of waves with a long tail (multi-GPU strips).
 template <bool kQuads, bool kSmem, int kMinBlocks, bool kPipe = false, int kT = kThreads>
 __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
-                                                                          const float4 *__restrict__ quads) {
+                                                                          const float4 *__restrict__ quads, int xSlices) {
   __shared__ StepRow sRows[kSmem ? kMaxSteps : 1];
   __shared__ DirEntry sDir[kSmem ? kGatherDirs : 1];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
-  const int tileX = blockIdx.x * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
+  // The 16 pattern classes of a tile are split into slices of CTAs. xSlices > 0: the slices of one tile are neighbours in blockIdx.x,
+  // so they run at the same time and share the tile's pyramid neighbourhood through L2; xSlices == 0: slices = gridDim.z (slowest).
+  const int nSlices = xSlices > 0 ? xSlices : (int)gridDim.z;
+  const int slice = xSlices > 0 ? (int)blockIdx.x % xSlices : (int)blockIdx.z;
+  const int tileX = (xSlices > 0 ? (int)blockIdx.x / xSlices : (int)blockIdx.x) * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
   const float vpx = a.viewport[0], vpy = a.viewport[1];
   const float invVpx = 1.0f / vpx, invVpy = 1.0f / vpy;
   const V3 cam = v3(a.cam[0], a.cam[1], a.cam[2]);
@@ -196,8 +200,8 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
   const uint2 *__restrict__ light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
   const int tx = 4 * (t & 15), ty = 4 * (t >> 4);
 
-  // gridDim.z splits the 16 pattern classes over CTAs (1, 2, 4, 8 or 16 slices): finer work units for grids of a few waves
-  const int idxPerCta = 16 / (int)gridDim.z, idx0 = (int)blockIdx.z * idxPerCta;
+  // 1, 2, 4, 8 or 16 slices: finer work units for grids of a few waves
+  const int idxPerCta = 16 / nSlices, idx0 = slice * idxPerCta;
 #pragma unroll 1
   for (int idx = idx0; idx < idx0 + idxPerCta; idx++) { // one pattern class per pass (CTA-uniform)
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
@@ -531,20 +535,23 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   // 4 slices of 4 pattern classes per tile: 4x more, 4x shorter work units (measured r01h: -5 % on a 4K frame, -14 % on an 8K strip of
   // 544 rows; 16 slices lose the L1 reuse between the passes of a tile and are slower on whole frames)
   static const int slices = getenv("LGCU_GATHER_SLICES") ? atoi(getenv("LGCU_GATHER_SLICES")) : 4; // development switch: 1, 2, 4, 8, 16
+  static const int sliceOrder = getenv("LGCU_GATHER_ORDER") ? atoi(getenv("LGCU_GATHER_ORDER")) : 1; // development switch: 0 = slices slowest (z), 1 = fastest (x)
+  const int xs = sliceOrder == 1 ? slices : 0;
+  const unsigned gx = sliceOrder == 1 ? grid.x * slices : grid.x, gz = sliceOrder == 1 ? 1 : slices;
   if (!scratch)
-    gatherFastKernel<false, false, 4><<<grid, kThreads, 0, s>>>(a, f, nullptr);
+    gatherFastKernel<false, false, 4><<<grid, kThreads, 0, s>>>(a, f, nullptr, 0);
   else if (variant == 1)
-    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
   else if (variant == 2)
-    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
   else if (variant == 4)
-    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
   else if (variant == 7)
-    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
   else if (smallTiles)
-    gatherFastKernel<true, false, 8, false, 128><<<dim3(grid.x, (rowsSpan + 31) / 32, slices), 128, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, false, 8, false, 128><<<dim3(gx, (rowsSpan + 31) / 32, gz), 128, 0, s>>>(a, f, quadsPtr, xs);
   else
-    gatherFastKernel<true, false, 4><<<dim3(grid.x, grid.y, slices), kThreads, 0, s>>>(a, f, quadsPtr);
+    gatherFastKernel<true, false, 4><<<dim3(gx, grid.y, gz), kThreads, 0, s>>>(a, f, quadsPtr, xs);
   return cudaGetLastError();
 }
 

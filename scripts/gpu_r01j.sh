@@ -9,7 +9,10 @@ timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo 
 cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_launch_$TAG.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gatherFast|rasterBig|rasterResolveFragments|frameFront" -s 8 -c 4 -f -o $OUT/frame_$TAG \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gatherFast|frameFront|frameChains|chainTail|packDepth|denoiseFinal" -s 12 -c 6 -f -o $OUT/frame_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_full_$TAG.log 2>&1
 tail -2 $OUT/ncu_full_$TAG.log | cut -c1-200
-ls -la $OUT/frame_$TAG.ncu-rep
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:raster -s 8 -c 8 -f -o $OUT/raster_$TAG \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_raster_$TAG.log 2>&1
+tail -2 $OUT/ncu_raster_$TAG.log | cut -c1-200
+ls -la $OUT/*_$TAG.ncu-rep
