@@ -5,10 +5,12 @@
 // instructions and load requests, not bytes:
 //
 //  * Pattern-coherent CTAs. The shader's 4x4 interleaved pattern gives every pixel with the same (x&3, y&3) the same march
-//    directions, step offsets and LODs. A CTA owns a 64x64 pixel tile and walks the 16 pattern classes in a CTA-uniform loop;
-//    in each pass thread t shades pixel (4*(t&15) + ox, 4*(t>>4) + oy). Direction, step offset, LOD and mip geometry are
+//    directions, step offsets and LODs. A CTA owns a 64x64 (or 64x32) pixel tile and walks pattern classes in a CTA-uniform
+//    loop; in each pass thread t shades pixel (4*(t&15) + ox, 4*(t>>4) + oy). Direction, step offset, LOD and mip geometry are
 //    therefore uniform-datapath operands, every level branch is uniform, and neighbouring lanes read neighbouring texels
-//    from LOD 2 upwards. The 16 passes of a CTA re-touch the same pyramid neighbourhood, which stays in L1.
+//    from LOD 2 upwards. The passes of a CTA re-touch the same pyramid neighbourhood, which stays in L1; the 16 classes of a
+//    tile are split over 4 CTAs that sit next to each other in the grid (finer work units for the tail of the grid, shared L2
+//    footprint: measured DRAM traffic of the launch = 1.18x its algorithmic bytes).
 //  * No transcendental per sample: pow/log (step offset, LOD, iteration count) come from host tables shared with the strict
 //    kernel (bit-identical level selection). The per-sample unprojection collapses to FMAs: the ray through pixel s is
 //    R(s) = Ra*sx + Rb*sy + Rc (affine in pixel coordinates), so along a march direction every dot product of the horizon test
@@ -157,41 +159,16 @@ __device__ __forceinline__ float4 mulMat4Exact(const Mat4 &M, float x, float y, 
 }
 __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)); }
 
-// One march sample in flight (software-pipelined variant): the footprints of both LOD levels and the raw quad taps, loaded one
-// step ahead so that the L1/L2 latency of step k+1 overlaps the horizon test and the hit body of step k.
-struct PendingSample {
-  Footprint f0, f1;
-  float4 q0, q1;
-};
-__device__ __forceinline__ PendingSample issueSample(const StepRow &st, const DirEntry &de, float px, float py, const float4 *__restrict__ quads) {
-  PendingSample p;
-  const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-  p.f0 = footprint(st.g0, sx, sy);
-  p.q0 = __ldg(quads + (unsigned)(st.g0.quadOfs + (p.f0.iy + 1) * st.g0.quadPitch + (p.f0.ix + 1)));
-  p.f1 = p.f0;
-  p.q1 = p.q0;
-  if (st.frac > 0.0f) { // uniform branch
-    p.f1 = footprint(st.g1, sx, sy);
-    p.q1 = __ldg(quads + (unsigned)(st.g1.quadOfs + (p.f1.iy + 1) * st.g1.quadPitch + (p.f1.ix + 1)));
-  }
-  return p;
-}
-__device__ __forceinline__ float bilerpQuad(const float4 &q, const Footprint &f) { return lerpf(lerpf(q.x, q.y, f.a), lerpf(q.z, q.w, f.a), f.b); }
-
 // kT = threads per CTA: a CTA shades a 64 x (kT / 4) pixel tile (256 -> 64x64, 128 -> 64x32). The smaller tile doubles the CTA count
 // for row strips and small frames, where the grid would otherwise be a couple of waves with a long tail (multi-GPU strips).
-template <bool kQuads, bool kSmem, int kMinBlocks, bool kPipe = false, int kT = kThreads>
+template <bool kQuads, int kMinBlocks, int kT>
 __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
                                                                           const float4 *__restrict__ quads, int xSlices) {
-  __shared__ StepRow sRows[kSmem ? kMaxSteps : 1];
-  __shared__ DirEntry sDir[kSmem ? kGatherDirs : 1];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
-  // The 16 pattern classes of a tile are split into slices of CTAs. xSlices > 0: the slices of one tile are neighbours in blockIdx.x,
-  // so they run at the same time and share the tile's pyramid neighbourhood through L2; xSlices == 0: slices = gridDim.z (slowest).
-  const int nSlices = xSlices > 0 ? xSlices : (int)gridDim.z;
-  const int slice = xSlices > 0 ? (int)blockIdx.x % xSlices : (int)blockIdx.z;
-  const int tileX = (xSlices > 0 ? (int)blockIdx.x / xSlices : (int)blockIdx.x) * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
+  // The 16 pattern classes of a tile are split over xSlices CTAs (0 or 1 = one CTA does all 16) that are neighbours in blockIdx.x
+  const int nSlices = xSlices > 0 ? xSlices : 1, slice = (int)blockIdx.x % nSlices;
+  const int tileX = ((int)blockIdx.x / nSlices) * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
   const float vpx = a.viewport[0], vpy = a.viewport[1];
   const float invVpx = 1.0f / vpx, invVpy = 1.0f / vpy;
   const V3 cam = v3(a.cam[0], a.cam[1], a.cam[2]);
@@ -200,22 +177,12 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
   const uint2 *__restrict__ light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
   const int tx = 4 * (t & 15), ty = 4 * (t >> 4);
 
-  // 1, 2, 4, 8 or 16 slices: finer work units for grids of a few waves
   const int idxPerCta = 16 / nSlices, idx0 = slice * idxPerCta;
 #pragma unroll 1
   for (int idx = idx0; idx < idx0 + idxPerCta; idx++) { // one pattern class per pass (CTA-uniform)
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
-    if (kSmem) { // this pass's table rows -> shared memory: the march then reads them with vector loads instead of LDCU + MOV
-      __syncthreads();
-      constexpr int kRowWords = kMaxSteps * (int)(sizeof(StepRow) / 4), kDirWords = kGatherDirs * (int)(sizeof(DirEntry) / 4);
-      const uint32_t *srcRows = reinterpret_cast<const uint32_t *>(&tb.row[idx * kMaxSteps]), *srcDir = reinterpret_cast<const uint32_t *>(&tb.dir[idx][0]);
-      for (int i = t; i < kRowWords; i += kT) reinterpret_cast<uint32_t *>(sRows)[i] = srcRows[i];
-      if (t < kDirWords) reinterpret_cast<uint32_t *>(sDir)[t] = srcDir[t];
-      __syncthreads();
-    } else if (!__any_sync(0xffffffffu, active)) {
-      continue;
-    }
+    if (!__any_sync(0xffffffffu, active)) continue;
     const int cx = active ? x : 0, cy = active ? y : a.rows.y0; // inactive lanes shade a valid pixel and discard it
     const float px = (float)cx + 0.5f, py = (float)cy + 0.5f;
     // --- centre reconstruction in the shader's order (:116-132, :182) -------------------------------------------------
@@ -235,11 +202,11 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const float n0 = sqrtf(q0);
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
     float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
-    const StepRow *__restrict__ rows = kSmem ? sRows : &tb.row[idx * kMaxSteps];
+    const StepRow *__restrict__ rows = &tb.row[idx * kMaxSteps];
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
-      const DirEntry de = kSmem ? sDir[d] : tb.dir[idx][d];
+      const DirEntry de = tb.dir[idx][d];
       const V3 Rd = v3(de.rdX, de.rdY, de.rdZ);
       // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
       const float q2 = de.q2, q1 = 2.0f * dotf(R0, Rd);
@@ -308,39 +275,18 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           my = hy;
         }
       };
-      if (kPipe && kQuads) {
-        // software-pipelined march, two steps per trip with ping-pong sample registers: the quad loads of step k+1 are in flight
-        // while step k runs its horizon test and hit body
-        auto consume = [&](int k, const PendingSample &ps) {
-          const StepRow &st = rows[k];
-          float z = bilerpQuad(ps.q0, ps.f0);
-          if (st.frac > 0.0f) z = fmaf(st.frac, bilerpQuad(ps.q1, ps.f1) - z, z); // :240
-          shade(k, st, ps.f0, ps.f1, z);
-        };
-        PendingSample sa, sb;
-        if (warpIters > 0) sa = issueSample(rows[0], de, px, py, quads);
 #pragma unroll 1
-        for (int k = 0; k < warpIters; k += 2) { // :214 (every branch here is warp-uniform)
-          if (k + 1 < warpIters) sb = issueSample(rows[k + 1], de, px, py, quads);
-          consume(k, sa);
-          if (k + 1 >= warpIters) break;
-          if (k + 2 < warpIters) sa = issueSample(rows[k + 2], de, px, py, quads);
-          consume(k + 1, sb);
+      for (int k = 0; k < warpIters; k++) { // :214
+        const StepRow &st = rows[k];
+        const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
+        const Footprint f0 = footprint(st.g0, sx, sy);
+        Footprint f1 = f0;
+        float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
+        if (st.frac > 0.0f) { // uniform branch
+          f1 = footprint(st.g1, sx, sy);
+          z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
         }
-      } else {
-#pragma unroll 1
-        for (int k = 0; k < warpIters; k++) { // :214
-          const StepRow &st = rows[k];
-          const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-          const Footprint f0 = footprint(st.g0, sx, sy);
-          Footprint f1 = f0;
-          float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
-          if (st.frac > 0.0f) { // uniform branch
-            f1 = footprint(st.g1, sx, sy);
-            z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
-          }
-          shade(k, st, f0, f1, z);
-        }
+        shade(k, st, f0, f1, z);
       }
       const float amb = -0.01f * cSum;
       sumX = fmaf(0.5f, Lx + amb, sumX); // :268
@@ -522,36 +468,27 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   FastTables f;
   if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, &f, nullptr)) return launchGatherStrict(a, t, s);
   const int rowsSpan = a.rows.y1 - (a.rows.y0 & ~3);
-  const dim3 grid((a.indirect.w + kTile - 1) / kTile, (rowsSpan + kTile - 1) / kTile);
-  static const int variant = getenv("LGCU_GATHER_VARIANT") ? atoi(getenv("LGCU_GATHER_VARIANT")) : 0; // development switch
+  const dim3 tiles((a.indirect.w + kTile - 1) / kTile, (rowsSpan + kTile - 1) / kTile);
   static const int smCount = [] {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
   const float4 *quadsPtr = static_cast<const float4 *>(scratch);
-  // fewer than ~6 waves of 64x64 tiles (4 CTAs per SM): use 64x32 tiles so that the tail of the last wave is half as long
-  const bool smallTiles = variant == 9 || (variant == 0 && (long long)grid.x * grid.y < 6LL * 4 * smCount); // variant 10 forces 64x64
-  // 4 slices of 4 pattern classes per tile: 4x more, 4x shorter work units (measured r01h: -5 % on a 4K frame, -14 % on an 8K strip of
-  // 544 rows; 16 slices lose the L1 reuse between the passes of a tile and are slower on whole frames)
-  static const int slices = getenv("LGCU_GATHER_SLICES") ? atoi(getenv("LGCU_GATHER_SLICES")) : 4; // development switch: 1, 2, 4, 8, 16
-  static const int sliceOrder = getenv("LGCU_GATHER_ORDER") ? atoi(getenv("LGCU_GATHER_ORDER")) : 1; // development switch: 0 = slices slowest (z), 1 = fastest (x)
-  const int xs = sliceOrder == 1 ? slices : 0;
-  const unsigned gx = sliceOrder == 1 ? grid.x * slices : grid.x, gz = sliceOrder == 1 ? 1 : slices;
-  if (!scratch)
-    gatherFastKernel<false, false, 4><<<grid, kThreads, 0, s>>>(a, f, nullptr, 0);
-  else if (variant == 1)
-    gatherFastKernel<true, false, 3><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
-  else if (variant == 2)
-    gatherFastKernel<true, true, 4><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
-  else if (variant == 4)
-    gatherFastKernel<true, false, 3, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
-  else if (variant == 7)
-    gatherFastKernel<true, false, 2, true><<<grid, kThreads, 0, s>>>(a, f, quadsPtr, 0);
-  else if (smallTiles)
-    gatherFastKernel<true, false, 8, false, 128><<<dim3(gx, (rowsSpan + 31) / 32, gz), 128, 0, s>>>(a, f, quadsPtr, xs);
+  if (!scratch) { // plain pyramids (lgcu_gi_gather without a scratch buffer): 64x64 tiles, all 16 pattern classes per CTA
+    gatherFastKernel<false, 4, kThreads><<<tiles, kThreads, 0, s>>>(a, f, nullptr, 0);
+    return cudaGetLastError();
+  }
+  // Work-unit granularity (measured, profiles/README.md): the 16 pattern classes of a tile are split over kSlices CTAs that are
+  // neighbours in blockIdx.x, so they run at the same time and share the tile's pyramid neighbourhood through L2 (-5 % on a 4K frame,
+  // -14 % on an 8K strip, DRAM traffic stays at the algorithmic bytes; 16 slices lose the L1 reuse between the passes of a tile);
+  // grids of fewer than ~6 waves of 64x64 tiles (row strips, small frames) use 64x32 tiles so that the last wave's tail is shorter.
+  constexpr int kSlices = 4;
+  const bool smallTiles = (long long)tiles.x * tiles.y < 6LL * 4 * smCount;
+  if (smallTiles)
+    gatherFastKernel<true, 8, 128><<<dim3(tiles.x * kSlices, (rowsSpan + 31) / 32), 128, 0, s>>>(a, f, quadsPtr, kSlices);
   else
-    gatherFastKernel<true, false, 4><<<dim3(gx, grid.y, gz), kThreads, 0, s>>>(a, f, quadsPtr, xs);
+    gatherFastKernel<true, 4, kThreads><<<dim3(tiles.x * kSlices, tiles.y), kThreads, 0, s>>>(a, f, quadsPtr, kSlices);
   return cudaGetLastError();
 }
 

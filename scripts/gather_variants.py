@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Time the GI gather kernel variant selected by LGCU_GATHER_VARIANT (development switch in csrc/k_gather_fast.cu) on one 4K frame:
-prints the per-pass GPU times of the fused frame (mean of N profiled frames) as one JSON line."""
+"""Per-pass GPU times of the fused frame (mean of N profiled frames), or of the gather stage on a row strip, as one JSON line:
+    python scripts/gather_variants.py [W H [row0 row1]]
+(Round 1 used it to A/B gather variants through development switches that have since been removed; the "variant" / "slices" /
+"order" keys of older profiles/*.jsonl refer to those.)"""
 import json
 import os
 import sys
