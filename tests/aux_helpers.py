@@ -65,3 +65,33 @@ def debug_tiles(count: int):
             x = pad
             y = f(y + f(size + pad))
     return out
+
+
+# ---- committed golden fixture of these passes (tests/golden/aux_passes.npz: outputs of the reference's own SPIR-V, make_golden.py) ----
+def load_aux_golden():
+    from pathlib import Path
+
+    return np.load(Path(__file__).resolve().parent / "golden" / "aux_passes.npz")
+
+
+def image_from_bytes(fmt: int, raw: np.ndarray, mips: int = 1) -> images.HostImage:
+    h, w = raw.shape[:2]
+    img = images.HostImage(fmt, w, h, mips)
+    img.level_bytes(0)[...] = raw
+    return img
+
+
+def golden_cases(z):
+    """Yields (name, run(backend) -> HostImage-or-bytes comparison) for every case of the aux fixture; `backend` has the pass
+    callables of include/lgcu.h minus the stream (an oracle, or an adapter over the CUDA library working on device copies)."""
+    k = 0
+    while f"interleave{k}.meta" in z:
+        fmt, W, H, gx, gy = (int(v) for v in z[f"interleave{k}.meta"])
+        yield ("interleave", k, fmt, (W, H, gx, gy))
+        k += 1
+    k = 0
+    while f"depthmip{k}.meta" in z:
+        fmt, W, H = (int(v) for v in z[f"depthmip{k}.meta"])
+        yield ("depthmip", k, fmt, (W, H))
+        k += 1
+    yield ("overlay", 0, abi.FORMAT_B8G8R8A8_SRGB, tuple(int(v) for v in z["overlay.meta"]))

@@ -33,7 +33,49 @@ FIXTURES = {
 }
 
 
+def aux_fixture() -> None:
+    """The passes either side of the hot path through the reference's own deinterleave.frag.spv,
+    interleave.frag.spv, mipLevelBuilder.frag.spv (Depth branch) and debugRenderer.frag.spv: inputs and outputs as raw storage bytes."""
+    import ctypes as C
+
+    from tests import aux_helpers as A
+
+    ref = loader.ref()
+    out = {}
+    for k, (fmt, W, H, gx, gy) in enumerate([(abi.FORMAT_R16G16B16A16_SFLOAT, 50, 29, 4, 4), (abi.FORMAT_R32G32_SFLOAT, 48, 32, 3, 2),
+                                             (abi.FORMAT_R32G32B32A32_SFLOAT, 17, 9, 4, 4)]):
+        src = A.random_image(fmt, W, H, seed=100 + k)
+        p = A.interleave_params(W, H, gx, gy)
+        out[f"interleave{k}.meta"] = np.array([fmt, W, H, gx, gy], dtype=np.int64)
+        out[f"interleave{k}.src"] = np.ascontiguousarray(src.level_bytes(0))
+        out[f"interleave{k}.deinterleaved"] = np.ascontiguousarray(A.run_pass(ref.deinterleave, p, src).level_bytes(0))
+        out[f"interleave{k}.interleaved"] = np.ascontiguousarray(A.run_pass(ref.interleave, p, src).level_bytes(0))
+    for k, (fmt, W, H) in enumerate([(abi.FORMAT_R16G16B16A16_SFLOAT, 33, 17), (abi.FORMAT_R32G32_SFLOAT, 64, 36)]):
+        src = A.random_depth_range_image(fmt, W, H, seed=200 + k)
+        img = images.HostImage(fmt, W, H, 2)
+        img.level_bytes(0)[...] = src.level_bytes(0)
+        mp = abi.MipLevelBuilderData(1.0)
+        assert ref.mip_level(C.byref(mp), C.byref(img.view(0, 1)), C.byref(img.view(1, 1)), None) == 0
+        out[f"depthmip{k}.meta"] = np.array([fmt, W, H], dtype=np.int64)
+        out[f"depthmip{k}.src"] = np.ascontiguousarray(img.level_bytes(0))
+        out[f"depthmip{k}.level1"] = np.ascontiguousarray(img.level_bytes(1))
+    W, H = 96, 54
+    target = A.random_image(abi.FORMAT_B8G8R8A8_SRGB, W, H, seed=300)
+    out["overlay.meta"] = np.array([W, H, 4], dtype=np.int64)
+    out["overlay.target_before"] = np.ascontiguousarray(target.level_bytes(0)).copy()
+    for k, quad in enumerate(A.debug_tiles(4)):
+        src = A.random_image(abi.FORMAT_R16G16B16A16_SFLOAT, W, H, seed=310 + k, lo=0.0, hi=1.5)
+        out[f"overlay.src{k}"] = np.ascontiguousarray(src.level_bytes(0))
+        out[f"overlay.quad{k}"] = np.array(list(quad.minmax), dtype=np.float32)
+        assert ref.debug_overlay(C.byref(quad), C.byref(src.view()), C.byref(target.view()), None) == 0
+    out["overlay.target_after"] = np.ascontiguousarray(target.level_bytes(0))
+    path = HERE / "aux_passes.npz"
+    np.savez_compressed(path, **out)
+    print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main() -> None:
+    aux_fixture()
     ref = loader.ref()
     for name, (seed, W, H, boxes, radius, shadow) in FIXTURES.items():
         sc = scene.make_scene(seed, W, H, n_boxes=boxes, shadow_size=shadow)

@@ -79,7 +79,7 @@ def assert_close(cuda_img, ref_img, level=0, what="", max_outside_frac=1e-4, min
 
 # ---- committed golden fixtures (tests/golden/*.npz, generated from the reference arm by tests/golden/make_golden.py) ----
 GOLDEN_DIR = __import__("pathlib").Path(__file__).resolve().parent / "golden"
-GOLDEN_NAMES = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
+GOLDEN_NAMES = sorted(p.stem for p in GOLDEN_DIR.glob("ssvgi_*.npz"))
 
 
 def load_golden(name: str):

@@ -118,3 +118,32 @@ def test_debug_tile_layout_matches_the_reference_loop():
     tiles = [tuple(round(v, 5) for v in t.minmax) for t in A.debug_tiles(10)]
     assert tiles[0] == (0.02, 0.02, 0.12, 0.12) and tiles[1] == (0.14, 0.02, 0.24, 0.12) and tiles[3] == (0.38, 0.02, 0.48, 0.12)
     assert tiles[8][0] == 0.02 and tiles[8][1] == 0.14  # 8 tiles fit in a row (0.02 + 8 * 0.12 = 0.98, the 9th would end at 1.08)
+
+
+def test_port_reproduces_reference_golden_fixture_of_the_aux_passes():
+    """tests/golden/aux_passes.npz holds what the reference's own SPIR-V produced (tests/golden/make_golden.py); the port must
+    reproduce it bit for bit — also where /root/reference and oracle/_ref are absent."""
+    z = A.load_aux_golden()
+    port = loader.port()
+    for kind, k, fmt, dims in A.golden_cases(z):
+        if kind == "interleave":
+            W, Hh, gx, gy = dims
+            src = A.image_from_bytes(fmt, z[f"interleave{k}.src"])
+            p = A.interleave_params(W, Hh, gx, gy)
+            assert np.array_equal(A.run_pass(port.deinterleave, p, src).level_bytes(0), z[f"interleave{k}.deinterleaved"]), (kind, k)
+            assert np.array_equal(A.run_pass(port.interleave, p, src).level_bytes(0), z[f"interleave{k}.interleaved"]), (kind, k)
+        elif kind == "depthmip":
+            img = A.image_from_bytes(fmt, z[f"depthmip{k}.src"], mips=2)
+            mp = abi.MipLevelBuilderData(1.0)
+            assert port.mip_level(C.byref(mp), C.byref(img.view(0, 1)), C.byref(img.view(1, 1)), None) == 0
+            want = images.HostImage(fmt, dims[0], dims[1], 2)
+            want.level_bytes(1)[...] = z[f"depthmip{k}.level1"]
+            assert A.equal_nan_aware(img, want, 1), (kind, k)
+        else:
+            W, Hh, tiles = dims
+            target = A.image_from_bytes(fmt, z["overlay.target_before"])
+            for t in range(tiles):
+                quad = abi.DebugQuadData((C.c_float * 4)(*[float(v) for v in z[f"overlay.quad{t}"]]))
+                src = A.image_from_bytes(abi.FORMAT_R16G16B16A16_SFLOAT, z[f"overlay.src{t}"])
+                assert port.debug_overlay(C.byref(quad), C.byref(src.view()), C.byref(target.view()), None) == 0
+            assert np.array_equal(target.level_bytes(0), z["overlay.target_after"])

@@ -128,3 +128,36 @@ def test_debug_overlay(cu, size, target_fmt):
         assert got.levels_equal(want, 0)
     below = int(0.2 * Hh)  # the four tiles end at y = 0.12: everything below keeps the target's contents (loadOp eLoad)
     assert np.array_equal(got.level_bytes(0)[below:], target_host.level_bytes(0)[below:])
+
+
+def test_cuda_reproduces_reference_golden_fixture_of_the_aux_passes(cu):
+    """The CUDA passes against tests/golden/aux_passes.npz (outputs of the reference's own SPIR-V): bit-exact; the sRGB8 overlay
+    target within one code."""
+    import torch
+
+    z = A.load_aux_golden()
+    for kind, k, fmt, dims in A.golden_cases(z):
+        if kind == "interleave":
+            W, Hh, gx, gy = dims
+            src = A.image_from_bytes(fmt, z[f"interleave{k}.src"])
+            p = A.interleave_params(W, Hh, gx, gy)
+            assert np.array_equal(_cuda_pass(cu.deinterleave, p, src).level_bytes(0), z[f"interleave{k}.deinterleaved"]), (kind, k)
+            assert np.array_equal(_cuda_pass(cu.interleave, p, src).level_bytes(0), z[f"interleave{k}.interleaved"]), (kind, k)
+        elif kind == "depthmip":
+            dev = images.DeviceImage.from_host(A.image_from_bytes(fmt, z[f"depthmip{k}.src"], mips=2))
+            mp = abi.MipLevelBuilderData(1.0)
+            cu.mip_level(C.byref(mp), C.byref(dev.view(0, 1)), C.byref(dev.view(1, 1)), None)
+            torch.cuda.synchronize()
+            want = images.HostImage(fmt, dims[0], dims[1], 2)
+            want.level_bytes(1)[...] = z[f"depthmip{k}.level1"]
+            assert A.equal_nan_aware(dev.to_host(), want, 1), (kind, k)
+        else:
+            W, Hh, tiles = dims
+            target = images.DeviceImage.from_host(A.image_from_bytes(fmt, z["overlay.target_before"]))
+            for t in range(tiles):
+                quad = abi.DebugQuadData((C.c_float * 4)(*[float(v) for v in z[f"overlay.quad{t}"]]))
+                src = images.DeviceImage.from_host(A.image_from_bytes(abi.FORMAT_R16G16B16A16_SFLOAT, z[f"overlay.src{t}"]))
+                cu.debug_overlay(C.byref(quad), C.byref(src.view()), C.byref(target.view()), None)
+                torch.cuda.synchronize()
+            d = np.abs(target.to_host().level_bytes(0).astype(np.int32) - z["overlay.target_after"].astype(np.int32))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-3
