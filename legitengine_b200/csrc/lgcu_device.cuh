@@ -128,6 +128,19 @@ __device__ __forceinline__ float linearToSrgb(float c) {
 __device__ __forceinline__ uint32_t packBgra8Srgb(float4 v) {
   return unorm8(linearToSrgb(v.z)) | (unorm8(linearToSrgb(v.y)) << 8) | (unorm8(linearToSrgb(v.x)) << 16) | (unorm8(saturatef(v.w)) << 24);
 }
+// The same conversion with the power function on the SFU (ex2.approx(lg2.approx(c) / 2.4), relative error ~1e-6 = 3e-4 of an 8-bit
+// code): the result differs from the libm-grade one only where the encoded value sits within that distance of a rounding boundary,
+// and then by one code — inside the +-1 LSB bar of the swapchain. The accurate powf costs ~40 instructions per channel, which makes
+// the final composite issue-bound instead of HBM-bound (ncu r01j: issue 73 %, DRAM 41 %).
+__device__ __forceinline__ float linearToSrgbFast(float c) {
+  if (!(c > 0.0f)) c = 0.0f;
+  if (c > 1.0f) c = 1.0f;
+  return c <= 0.0031308f ? 12.92f * c : 1.055f * __powf(c, 1.0f / 2.4f) - 0.055f;
+}
+template <bool kFast> __device__ __forceinline__ uint32_t packBgra8SrgbT(float4 v) {
+  if (!kFast) return packBgra8Srgb(v);
+  return unorm8(linearToSrgbFast(v.z)) | (unorm8(linearToSrgbFast(v.y)) << 8) | (unorm8(linearToSrgbFast(v.x)) << 16) | (unorm8(saturatef(v.w)) << 24);
+}
 
 // ---- exact-order bilinear / trilinear (strict kernels; compile the TU with -fmad=false) ---------------------------
 // lerp(p, q, t) = p + (q - p) * t; bilinear = lerp(lerp(t00, t10, a), lerp(t01, t11, a), b).
