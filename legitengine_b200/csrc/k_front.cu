@@ -13,6 +13,8 @@
 //    shared memory. Every level is rounded to its storage format (fp16 for the light chain) before it feeds the next one
 //    and the four taps are summed in the shader's order, so the result is bit-identical to the nine separate passes.
 // Compiled with -fmad=false (shader-order fp32, see lgcu_shading.cuh).
+#include <cstdlib>
+
 #include "lgcu_shading.cuh"
 
 namespace lgcu {
@@ -22,6 +24,7 @@ namespace {
 using namespace shading;
 
 constexpr int kTileW = 64, kTileH = 16, kThreads = 256;
+constexpr int kFrontBlocksPerSmDefault = 2; // resident CTAs per SM (register budget), see frameFrontKernel
 
 struct MipTexel { // one texel of both chains, in storage form
   uint2 light;    // RGBA16F
@@ -68,7 +71,8 @@ __device__ __forceinline__ void storePair(const LevelView &l, int x, int y, uint
 }
 __device__ __forceinline__ uint2 asBits(float2 v) { return make_uint2(__float_as_uint(v.x), __float_as_uint(v.y)); }
 
-__global__ void __launch_bounds__(kThreads, 2) frameFrontKernel(const __grid_constant__ FrontArgs a) {
+// kMinBlocks = resident CTAs per SM the register allocation aims for: 2 -> 118 registers, 3 -> 78, 4 -> 64 (16 bytes of spills)
+template <int kMinBlocks> __global__ void __launch_bounds__(kThreads, kMinBlocks) frameFrontKernel(const __grid_constant__ FrontArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ MipTexel s2[kTileH / 4][kTileW / 4]; // level-2 texels of the tile (4 x 16)
   __shared__ MipTexel s3[kTileH / 8][kTileW / 8]; // level-3 texels (2 x 8)
@@ -156,9 +160,15 @@ cudaError_t launchFrameFront(const FrontArgs &args, int smCount, cudaStream_t s)
   a.tilesY = (a.g.rows.y1 - a.g.rows.y0 + kTileH - 1) / kTileH;
   a.tileCount = a.tilesX * a.tilesY;
   const size_t smem = a.g.nObjects <= (uint32_t)kMaxSharedObjects ? (size_t)a.g.nObjects * sizeof(ObjectColors) : 0;
-  int grid = smCount * 4; // two resident CTAs per SM, two rounds: evens out the tail without re-staging the table often
+  static const int blocksPerSm = getenv("LGCU_FRONT_BLOCKS") ? atoi(getenv("LGCU_FRONT_BLOCKS")) : kFrontBlocksPerSmDefault; // development switch: 2, 3, 4
+  int grid = smCount * blocksPerSm * 2; // the resident CTAs per SM, two rounds: evens out the tail without re-staging the table often
   if (grid > a.tileCount) grid = a.tileCount;
-  frameFrontKernel<<<grid, kThreads, smem, s>>>(a);
+  if (blocksPerSm == 3)
+    frameFrontKernel<3><<<grid, kThreads, smem, s>>>(a);
+  else if (blocksPerSm == 4)
+    frameFrontKernel<4><<<grid, kThreads, smem, s>>>(a);
+  else
+    frameFrontKernel<2><<<grid, kThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
