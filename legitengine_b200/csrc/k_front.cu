@@ -24,7 +24,7 @@ namespace {
 using namespace shading;
 
 constexpr int kTileW = 64, kTileH = 16, kThreads = 256;
-constexpr int kFrontBlocksPerSmDefault = 2; // resident CTAs per SM (register budget), see frameFrontKernel
+constexpr int kFrontBlocksPerSmDefault = 4; // resident CTAs per SM (register budget); measured r01n at 4K: 2 -> 0.220 ms, 3 -> 0.189, 4 -> 0.182
 
 struct MipTexel { // one texel of both chains, in storage form
   uint2 light;    // RGBA16F
@@ -71,7 +71,8 @@ __device__ __forceinline__ void storePair(const LevelView &l, int x, int y, uint
 }
 __device__ __forceinline__ uint2 asBits(float2 v) { return make_uint2(__float_as_uint(v.x), __float_as_uint(v.y)); }
 
-// kMinBlocks = resident CTAs per SM the register allocation aims for: 2 -> 118 registers, 3 -> 78, 4 -> 64 (16 bytes of spills)
+// kMinBlocks = resident CTAs per SM the register allocation aims for: 2 -> 118 registers, 3 -> 78, 4 -> 64 (16 bytes of spills). The
+// kernel is bound by latency (a long per-pixel chain behind four 16-byte loads), so more resident warps beat fewer spills.
 template <int kMinBlocks> __global__ void __launch_bounds__(kThreads, kMinBlocks) frameFrontKernel(const __grid_constant__ FrontArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   __shared__ MipTexel s2[kTileH / 4][kTileW / 4]; // level-2 texels of the tile (4 x 16)

@@ -29,7 +29,6 @@
 //    1/sample distance), so the two variants see the same centre.
 #include <cmath>
 #include <cstdlib>
-#include <type_traits>
 
 #include "lgcu_kernels.h"
 
@@ -37,7 +36,6 @@ namespace lgcu {
 
 namespace {
 
-constexpr bool kGatherSpecialisedDefault = false; // clamp-free / side-one step specialisations (kFast): off until measured on the GPU
 constexpr int kTile = 64;      // pixels per tile edge
 constexpr int kThreads = 256;  // 16x16 pixels of one pattern class per pass
 constexpr int kMaxSteps = 12;  // march steps the tables hold (8 are reached for landscape viewports at any resolution)
@@ -110,14 +108,9 @@ struct Footprint {
   int ix, iy;
   float a, b;
 };
-// kNoClamp: the caller has proved (CTA-uniformly) that the coordinate clamp does not bind for any of its lanes
-template <bool kNoClamp = false> __device__ __forceinline__ Footprint footprint(const LevelGeom &g, float sx, float sy) {
+__device__ __forceinline__ Footprint footprint(const LevelGeom &g, float sx, float sy) {
   Footprint f;
-  float u = fmaf(sx, g.scaleX, -0.5f), v = fmaf(sy, g.scaleY, -0.5f);
-  if (!kNoClamp) {
-    u = fminf(fmaxf(u, -1.0f), g.maxX);
-    v = fminf(fmaxf(v, -1.0f), g.maxY);
-  }
+  const float u = fminf(fmaxf(fmaf(sx, g.scaleX, -0.5f), -1.0f), g.maxX), v = fminf(fmaxf(fmaf(sy, g.scaleY, -0.5f), -1.0f), g.maxY);
   const float tu = __fadd_rd(u, kFloorMagic), tv = __fadd_rd(v, kFloorMagic);
   f.a = u - (tu - kFloorMagic);
   f.b = v - (tv - kFloorMagic);
@@ -140,9 +133,8 @@ __device__ __forceinline__ float fetchDepth(const LevelGeom &g, const Footprint 
   return lerpf(lerpf(t00, t10, f.a), lerpf(t01, t11, f.a), f.b);
 }
 
-template <bool kNoClamp = false> __device__ __forceinline__ float3 fetchLight(const LevelGeom &g, const Footprint &f, const uint2 *__restrict__ light) {
-  const int x0 = kNoClamp ? f.ix : max(f.ix, 0), x1 = kNoClamp ? f.ix + 1 : min(f.ix + 1, g.wm1);
-  const int y0 = kNoClamp ? f.iy : max(f.iy, 0), y1 = kNoClamp ? f.iy + 1 : min(f.iy + 1, g.hm1);
+__device__ __forceinline__ float3 fetchLight(const LevelGeom &g, const Footprint &f, const uint2 *__restrict__ light) {
+  const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, g.wm1), y0 = max(f.iy, 0), y1 = min(f.iy + 1, g.hm1);
   const unsigned o0 = g.texOfs + y0 * g.texPitch, o1 = g.texOfs + y1 * g.texPitch;
   const uint2 r00 = __ldg(&light[o0 + x0]), r10 = __ldg(&light[o0 + x1]), r01 = __ldg(&light[o1 + x0]), r11 = __ldg(&light[o1 + x1]);
   const float2 a00 = __half22float2(*reinterpret_cast<const __half2 *>(&r00.x)), a10 = __half22float2(*reinterpret_cast<const __half2 *>(&r10.x));
@@ -169,11 +161,7 @@ __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd
 
 // kT = threads per CTA: a CTA shades a 64 x (kT / 4) pixel tile (256 -> 64x64, 128 -> 64x32). The smaller tile doubles the CTA count
 // for row strips and small frames, where the grid would otherwise be a couple of waves with a long tail (multi-GPU strips).
-// kFast: per pass, every (direction, step) pair is classified CTA-uniformly (one pair per lane, two ballots): "clamp-free" = the
-// bilinear footprints of ALL the CTA's pixels lie strictly inside both LOD levels, so neither the coordinate clamp nor the tap
-// clamps can bind; "side-one" = all samples lie in uv [0.1, 0.9]², where the product of saturates of :220-228 is exactly 1. The march
-// then runs the matching specialisation of the step body. Values are identical to the general path; only dead clamps are skipped.
-template <bool kQuads, int kMinBlocks, int kT, bool kFast = false>
+template <bool kQuads, int kMinBlocks, int kT>
 __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
                                                                           const float4 *__restrict__ quads, int xSlices) {
   const int t = threadIdx.x;
@@ -195,8 +183,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
     if (!__any_sync(0xffffffffu, active)) continue;
-    // inactive lanes shade a valid pixel and discard it; with kFast that pixel stays inside the tile's box, which the classification covers
-    const int cx = active ? x : (kFast ? min(x, a.indirect.w - 1) : 0), cy = active ? y : (kFast ? min(max(y, a.rows.y0), a.rows.y1 - 1) : a.rows.y0);
+    const int cx = active ? x : 0, cy = active ? y : a.rows.y0; // inactive lanes shade a valid pixel and discard it
     const float px = (float)cx + 0.5f, py = (float)cy + 0.5f;
     // --- centre reconstruction in the shader's order (:116-132, :182) -------------------------------------------------
     const float cu = __fdiv_rn(px, vpx), cv = __fdiv_rn(py, vpy);
@@ -216,28 +203,6 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
     float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
     const StepRow *__restrict__ rows = &tb.row[idx * kMaxSteps];
-    unsigned clampFree = 0u, sideOne = 0u; // bit d * 8 + k
-    if (kFast && kQuads && tb.maxSteps <= 8) {
-      const int lane = t & 31, cd = lane >> 3, ck = lane & 7;
-      bool cf = false, so = false;
-      if (ck < tb.maxSteps) {
-        const StepRow &st = rows[ck];
-        const float dx = tb.dir[idx][cd].dirX, dy = tb.dir[idx][cd].dirY;
-        // every pixel centre a lane of this CTA can hold (active or re-homed inactive lanes) lies in the tile's box
-        // [tileX + 0.5, tileX + 63.5] x [tileY + 0.5, tileY + kT/4 - 0.5]; fmaf(dir, off, centre) is monotone in the centre
-        const float px0 = (float)tileX + 0.5f, py0 = (float)tileY + 0.5f;
-        const float sx0 = fmaf(dx, st.off, px0), sx1 = fmaf(dx, st.off, px0 + (float)(kTile - 1));
-        const float sy0 = fmaf(dy, st.off, py0), sy1 = fmaf(dy, st.off, py0 + (float)(kT / 4 - 1));
-        auto inside = [&](const LevelGeom &lg) { // the expressions of footprint(): floor(u) in [0, w - 2] for every lane
-          return fmaf(sx0, lg.scaleX, -0.5f) >= 0.0f && fmaf(sx1, lg.scaleX, -0.5f) < lg.maxX && fmaf(sy0, lg.scaleY, -0.5f) >= 0.0f &&
-                 fmaf(sy1, lg.scaleY, -0.5f) < lg.maxY;
-        };
-        cf = inside(st.g0) && inside(st.g1);
-        so = sx0 * invVpx >= 0.1001f && sx1 * invVpx <= 0.8999f && sy0 * invVpy >= 0.1001f && sy1 * invVpy <= 0.8999f;
-      }
-      clampFree = __ballot_sync(0xffffffffu, cf);
-      sideOne = __ballot_sync(0xffffffffu, so) & clampFree;
-    }
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
@@ -275,8 +240,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
 
       const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
       // horizon test + hit body of one march sample whose depth z is known (:241-263)
-      auto shade = [&](auto noClampTag, auto sideOneTag, int k, const StepRow &st, const Footprint &f0, const Footprint &f1, float z) {
-        constexpr bool kNoClamp = decltype(noClampTag)::value, kSideOne = decltype(sideOneTag)::value;
+      auto shade = [&](int k, const StepRow &st, const Footprint &f0, const Footprint &f1, float z) {
         const float zs = z * fastRsqrt(fmaf(st.off, fmaf(st.off, q2, q1), q0)); // z / |R(s)|
         const float hx = fmaf(zs, fmaf(st.off, xRd, xR0), xE); // dot(eye, P - C)      :241-252
         const float hy = fmaf(zs, fmaf(st.off, yRd, yR0), yE); // dot(tangent, P - C)
@@ -288,16 +252,13 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           const float inv = fastRcp(fmaxf(fmaf(hx, hx, hy * hy), 1e-37f));
           const float c2 = (hx * hx - hy * hy) * inv, s2 = 2.0f * hx * hy * inv;
           const float hc = eN4 * (c2 - c2m) + tN4 * (((2.0f * maxH - 2.0f * h) - s2m) + s2); // :44-49
-          float side = 1.0f;
-          if (!kSideOne) {
-            const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-            const float su = sx * invVpx, sv = sy * invVpy;
-            // product of the four saturates of :220-228 (at most one per axis is below 1)
-            side = saturatef(fminf(su, 1.0f - su) * 10.0f) * saturatef(fminf(sv, 1.0f - sv) * 10.0f);
-          }
-          float3 ls = fetchLight<kNoClamp>(st.g0, f0, light); // :256
+          const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
+          const float su = sx * invVpx, sv = sy * invVpy;
+          // product of the four saturates of :220-228 (at most one per axis is below 1)
+          const float side = saturatef(fminf(su, 1.0f - su) * 10.0f) * saturatef(fminf(sv, 1.0f - sv) * 10.0f);
+          float3 ls = fetchLight(st.g0, f0, light); // :256
           if (st.frac > 0.0f) {
-            const float3 hi = fetchLight<kNoClamp>(st.g1, f1, light);
+            const float3 hi = fetchLight(st.g1, f1, light);
             ls.x = fmaf(st.frac, hi.x - ls.x, ls.x);
             ls.y = fmaf(st.frac, hi.y - ls.y, ls.y);
             ls.z = fmaf(st.frac, hi.z - ls.z, ls.z);
@@ -314,30 +275,18 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           my = hy;
         }
       };
-      auto marchStep = [&](auto noClampTag, auto sideOneTag, int k) {
-        constexpr bool kNoClamp = decltype(noClampTag)::value;
+#pragma unroll 1
+      for (int k = 0; k < warpIters; k++) { // :214
         const StepRow &st = rows[k];
         const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-        const Footprint f0 = footprint<kNoClamp>(st.g0, sx, sy);
+        const Footprint f0 = footprint(st.g0, sx, sy);
         Footprint f1 = f0;
         float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
         if (st.frac > 0.0f) { // uniform branch
-          f1 = footprint<kNoClamp>(st.g1, sx, sy);
+          f1 = footprint(st.g1, sx, sy);
           z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
         }
-        shade(noClampTag, sideOneTag, k, st, f0, f1, z);
-      };
-      using No = std::integral_constant<bool, false>;
-      using Yes = std::integral_constant<bool, true>;
-#pragma unroll 1
-      for (int k = 0; k < warpIters; k++) { // :214
-        const unsigned bit = 1u << ((d * 8 + k) & 31);
-        if (kFast && (sideOne & bit)) // CTA-uniform branches
-          marchStep(Yes{}, Yes{}, k);
-        else if (kFast && (clampFree & bit))
-          marchStep(Yes{}, No{}, k);
-        else
-          marchStep(No{}, No{}, k);
+        shade(k, st, f0, f1, z);
       }
       const float amb = -0.01f * cSum;
       sumX = fmaf(0.5f, Lx + amb, sumX); // :268
@@ -536,16 +485,10 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   // grids of fewer than ~6 waves of 64x64 tiles (row strips, small frames) use 64x32 tiles so that the last wave's tail is shorter.
   constexpr int kSlices = 4;
   const bool smallTiles = (long long)tiles.x * tiles.y < 6LL * 4 * smCount;
-  static const bool specialised = getenv("LGCU_GATHER_SPECIALISED") ? atoi(getenv("LGCU_GATHER_SPECIALISED")) != 0 : kGatherSpecialisedDefault;
-  const dim3 gridSmall(tiles.x * kSlices, (rowsSpan + 31) / 32), gridBig(tiles.x * kSlices, tiles.y);
-  if (smallTiles && specialised)
-    gatherFastKernel<true, 8, 128, true><<<gridSmall, 128, 0, s>>>(a, f, quadsPtr, kSlices);
-  else if (smallTiles)
-    gatherFastKernel<true, 8, 128><<<gridSmall, 128, 0, s>>>(a, f, quadsPtr, kSlices);
-  else if (specialised)
-    gatherFastKernel<true, 4, kThreads, true><<<gridBig, kThreads, 0, s>>>(a, f, quadsPtr, kSlices);
+  if (smallTiles)
+    gatherFastKernel<true, 8, 128><<<dim3(tiles.x * kSlices, (rowsSpan + 31) / 32), 128, 0, s>>>(a, f, quadsPtr, kSlices);
   else
-    gatherFastKernel<true, 4, kThreads><<<gridBig, kThreads, 0, s>>>(a, f, quadsPtr, kSlices);
+    gatherFastKernel<true, 4, kThreads><<<dim3(tiles.x * kSlices, tiles.y), kThreads, 0, s>>>(a, f, quadsPtr, kSlices);
   return cudaGetLastError();
 }
 
