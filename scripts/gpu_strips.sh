@@ -1,12 +1,12 @@
 #!/bin/bash
-# r01i (2 GPUs): all GPU tests incl. the multi-GPU ones, then the strips bench with cost-aware bounds at N GPUs.
-TAG=${1:-r01i}; N=${2:-2}
+# ONE frame in row strips over N GPUs (p2p transport, cost-aware bounds, per-rank stage profile).
+# Usage: gpurun --gpus N -- 'bash scripts/gpu_strips.sh TAG N "8k 4k"'
+TAG=${1:-s}; N=${2:-8}; WL=${3:-"8k"}
 OUT=gpurun_out; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
-tail -4 $OUT/pytest_gpu_$TAG.log
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N "$@"; }
-run --workload 8k --shard strips --transport p2p --steps 40 --warmup 5 > $OUT/strips8k_n${N}_$TAG.json 2> $OUT/strips8k_n${N}_$TAG.err
-python - "$OUT/strips8k_n${N}_$TAG.json" <<'PY'
+for w in $WL; do
+  run --workload $w --shard strips --transport p2p --steps 40 --warmup 5 > $OUT/strips${w}_n${N}_$TAG.json 2> $OUT/strips${w}_n${N}_$TAG.err
+  python - "$OUT/strips${w}_n${N}_$TAG.json" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
@@ -15,4 +15,5 @@ try:
     for b in d.get("balance") or []: print("   balance", b)
 except Exception as e: print(sys.argv[1], "ERR", e)
 PY
-grep -v "^\*\|OMP_NUM\|^$" $OUT/strips8k_n${N}_$TAG.err | tail -8
+  grep -v "^\*\|OMP_NUM\|^$" $OUT/strips${w}_n${N}_$TAG.err | tail -5
+done

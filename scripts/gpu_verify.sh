@@ -1,6 +1,7 @@
 #!/bin/bash
-# r01j: final verification of the round: all GPU tests, smoke(), default bench line, ncu launch list, full capture of the gather and of the raster kernels.
-TAG=${1:-r01j}
+# Verification of a tree on one B200 (gpurun -- 'bash scripts/gpu_verify.sh TAG'): all GPU tests, smoke(), default bench line, ncu launch
+# list, ncu --set full of one frame's kernels and of one mesh frame's raster kernels. Condense with scripts/ncu_summary.py into profiles/.
+TAG=${1:-verify}
 OUT=gpurun_out; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_$TAG.log
 tail -4 $OUT/pytest_gpu_$TAG.log

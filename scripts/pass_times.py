@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Per-pass GPU times of the fused frame (mean of N profiled frames), or of the gather stage on a row strip, as one JSON line:
-    python scripts/gather_variants.py [W H [row0 row1]]
-(Round 1 used it to A/B gather variants through development switches that have since been removed; the "variant" / "slices" /
-"order" keys of older profiles/*.jsonl refer to those.)"""
+    python scripts/pass_times.py [W H [row0 row1]]
+Used for A/B runs of switch-guarded kernel changes (LGCU_FAST_SRGB, LGCU_FRONT_BLOCKS, LGCU_RASTER_PATH: the switches that exist are
+echoed into the line). Round 1 also A/B-ed gather variants through switches that have since been removed; the "variant" / "slices" /
+"order" / "specialised" keys of profiles/r01*.jsonl refer to those (profiles/README.md says what each one was)."""
 import json
 import os
 import sys
@@ -53,4 +54,4 @@ else:
         ev1.record(stream)
     r.sync()
     acc["GatherStage(rows %d..%d)" % ROWS] = ev0.elapsed_time(ev1) / n
-print(json.dumps({"specialised": os.environ.get("LGCU_GATHER_SPECIALISED", "default"), "fast_srgb": os.environ.get("LGCU_FAST_SRGB", "default"), "front_blocks": os.environ.get("LGCU_FRONT_BLOCKS", "default"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
+print(json.dumps({"fast_srgb": os.environ.get("LGCU_FAST_SRGB", "default"), "front_blocks": os.environ.get("LGCU_FRONT_BLOCKS", "default"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
