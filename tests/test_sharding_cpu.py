@@ -97,7 +97,7 @@ def _oracle_stage(be, fi, p, inp, stage, rows, W, Hh):
         be.final_gather(C.byref(p.final), _v(fi.directLight), _v(fi.blurredDirectLight), _v(fi.albedo), _v(fi.denoisedIndirectLight), _v(fi.swapchain), r)
 
 
-def _worker(rank, world, port, W, Hh, result_dir):
+def _worker(rank, world, port, W, Hh, result_dir, uneven=False):
     import torch
     import torch.distributed as dist
 
@@ -116,6 +116,9 @@ def _worker(rank, world, port, W, Hh, result_dir):
         fi = passes.FrameImages(W, Hh, images.HostImage, shadow_size=128)  # poison-filled: rows that never arrive stay 0xCD
         inp = passes.upload_inputs(fi, sc)
         bounds = sharding.strip_bounds(Hh, world)
+        if uneven:  # cost-aware boundaries: the plans must still deliver every halo row
+            bounds = sharding.rebalance_bounds(bounds, [1.0 + 1.5 * r for r in range(world)], Hh)
+            assert bounds != sharding.strip_bounds(Hh, world)
         rows = bounds[rank]
         views = {n: (torch.from_numpy(getattr(fi, n).buf), getattr(fi, n).desc) for n in multigpu.StripRenderer.EXCHANGED}
         _oracle_stage(be, fi, p, inp, "front", rows, W, Hh)
@@ -142,12 +145,12 @@ def _worker(rank, world, port, W, Hh, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,size", [(2, (96, 80)), (3, (160, 112))])
-def test_strip_pipeline_gloo(world, size, tmp_path):
+@pytest.mark.parametrize("world,size,uneven", [(2, (96, 80), False), (3, (160, 112), False), (3, (160, 112), True)])
+def test_strip_pipeline_gloo(world, size, uneven, tmp_path):
     import torch.multiprocessing as mp
 
     W, Hh = size
-    mp.spawn(_worker, args=(world, _free_port(), W, Hh, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), W, Hh, str(tmp_path), uneven), nprocs=world, join=True)
     for rank in range(world):
         assert (tmp_path / f"rank{rank}.txt").read_text() == "ok"
 
