@@ -60,10 +60,11 @@ def build_cuda(force: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "lgcu.h"]
     objs = []
-    with open(LIB / "nvcc_ptxas.log", "a") as log:
+    with open(LIB / "nvcc_ptxas.log", "a") as log:  # ptxas -v output (registers, spills) of the units compiled by this call; git-ignored
         for unit, extra in CUDA_UNITS.items():
             src, obj = CSRC / unit, OBJ / (unit + ".o")
             if force or _stale(obj, [src] + headers):
+                log.write(f"==== {unit}\n")
                 _run([NVCC] + NVCC_COMMON + extra + ["-c", src, "-o", obj], log=log)
             objs.append(obj)
         out = LIB / "liblgcu.so"
