@@ -121,3 +121,62 @@ def oracle_mesh_frame(seed: int, width: int, height: int, camera_key: Tuple = No
     fi = passes.FrameImages(width, height, images.HostImage)
     passes.run_pass_list(port, fi, p, passes.upload_inputs(fi, sc))
     return mesh, camera, sc, p, fi
+
+
+# ---- full-size frames: whole-frame oracle for the cheap passes, row strips for the expensive ones ----
+def oracle_frame_on_strips(seed: int, width: int, height: int, strips):
+    """Oracle images of a big frame in seconds: K1..K4 (streaming passes) over the whole frame, K5..K7 (gather, denoise, final) only
+    on the given row strips — the oracle's passes take the same lgcu_rows as the CUDA ones. Rows outside the strips stay poisoned."""
+    sc = scene.make_scene(seed, width, height)
+    p = passes.make_params(width, height, sc.matrices, 0)
+    fi = passes.FrameImages(width, height, images.HostImage)
+    inp = passes.upload_inputs(fi, sc)
+    be = loader.port()
+    passes.run_pass_list(be, fi, p, inp, stop_after="blur")
+    v = lambda img, base=0, n=None: C.byref(img.view(base, n))
+    for rows in strips:
+        r = C.byref(abi.LgcuRows(*rows))
+        assert be.gi_gather(C.byref(p.indirect), v(fi.blurredDirectLight), v(fi.blurredDepthMoments), v(fi.normal), v(fi.depthStencil), v(fi.indirectLight), 0, r) == 0
+        assert be.denoise(C.byref(p.denoiser), v(fi.indirectLight), v(fi.normal), v(fi.depthMoments), v(fi.denoisedIndirectLight), r) == 0
+        assert be.final_gather(C.byref(p.final), v(fi.directLight), v(fi.blurredDirectLight), v(fi.albedo), v(fi.denoisedIndirectLight), v(fi.swapchain), r) == 0
+    return sc, p, fi
+
+
+def rows_close(got: images.HostImage, want: images.HostImage, y0: int, y1: int, what: str, max_outside_frac: float = 1e-3, min_psnr: float = 60.0, level: int = 0):
+    """assert_close restricted to rows [y0, y1) of one level (north-star tolerance: 1e-3 or one fp16 ulp of the value, PSNR >= 60 dB)."""
+    a, b = got.level_f32(level)[y0:y1], want.level_f32(level)[y0:y1]
+    tol = np.maximum(1e-3, F16_EPS * np.abs(b))
+    outside = float((np.abs(a - b) > tol).any(axis=2).mean())
+    assert outside <= max_outside_frac, f"{what} rows [{y0},{y1}): {outside:.2e} of the texels outside the tolerance"
+    # PSNR against a peak of at least 1.0: a dark strip must not turn the 60 dB bar into something stricter than max-abs 1e-3
+    peak = max(1.0, float(np.max(np.abs(b))))
+    assert psnr(a, b, peak) >= min_psnr, f"{what} rows [{y0},{y1}): PSNR {psnr(a, b, peak):.1f} dB"
+
+
+def check_big_frame(get_image, ref: passes.FrameImages, strips, width: int, height: int, whole_frame_images=True):
+    """Parity of a full-size frame: `get_image(name)` returns the device frame's HostImage. G-buffer and the depth-moment chains are
+    bit-exact over the whole frame (every level); the light chains within tolerance; gather / denoise / swapchain on `strips`."""
+    levels = passes.mip_levels_built(width, height)
+    if whole_frame_images:
+        for name in ("normal", "depthStencil"):
+            assert_bit_exact(get_image(name), getattr(ref, name), 0, name)
+        for name in ("albedo", "emissive"):  # pow(colour, 2.2) per object: libm vs device pow, then fp16 rounding (as in test_gbuffer_resolve)
+            r = compare_level(get_image(name), getattr(ref, name), 0)
+            assert r["outside_tol"] == 0 and r["mismatched_texels"] <= 0.02 * r["texels"], (name, r)
+        for name in ("depthMoments", "blurredDepthMoments"):
+            got = get_image(name)
+            for l in range(levels):
+                assert_bit_exact(got, getattr(ref, name), l, name)
+        for name in ("directLight", "blurredDirectLight"):
+            got = get_image(name)
+            for l in range(levels):
+                w, h = images.mip_size(width, height, l)
+                if w * h >= 4096:  # one texel of a tiny level is already more than the allowed fraction
+                    rows_close(got, getattr(ref, name), 0, h, f"{name} level {l}", level=l)
+    indirect, denoised, swap = get_image("indirectLight"), get_image("denoisedIndirectLight"), get_image("swapchain")
+    for y0, y1 in strips:
+        rows_close(indirect, ref.indirectLight, y0, y1, "indirectLight")
+        rows_close(denoised, ref.denoisedIndirectLight, y0, y1, "denoisedIndirectLight")
+        a = swap.level_raw(0)[y0:y1].astype(np.int32)
+        b = ref.swapchain.level_raw(0)[y0:y1].astype(np.int32)
+        assert (np.abs(a - b) > 1).mean() < 1e-3, f"swapchain rows [{y0},{y1})"

@@ -178,3 +178,15 @@ def test_hammersley_table_and_march_schedule():
             if lod_want is not None:
                 lod = np.log(max(0.0, 1.57075 * (float(off) - 1.0) * 0.5)) / 0.693147182 - 2.0
                 assert abs(lod - lod_want) < 0.01, (W, k, lod)
+
+
+def test_big_frame_checker_on_the_oracle_itself():
+    """The full-size parity helper (tests/helpers.py: oracle on row strips + check_big_frame) agrees with the whole-frame oracle:
+    what the -m gpu test uses at 4K / 8K, exercised here at a small size with the oracle's own frame standing in for the device's."""
+    W, Hh = 320, 180
+    strips = ((0, 16), (80, 96), (164, 180))
+    sc, p, ref = H.oracle_frame_on_strips(11, W, Hh, strips)
+    whole_sc, whole_p, whole = H.oracle_frame(11, W, Hh)
+    H.check_big_frame(lambda name: getattr(whole, name), ref, strips, W, Hh)
+    # rows outside the strips were not computed by the strip oracle (poison), so the checker really only looks at the strips
+    assert not np.array_equal(ref.indirectLight.level_bytes(0)[40:60], whole.indirectLight.level_bytes(0)[40:60])

@@ -210,3 +210,19 @@ def test_interleave_builder_on_the_rendergraph(grid):
     if W % gx == 0 and Hh % gy == 0:
         assert np.array_equal(back, src)
     r.close()
+
+
+@pytest.mark.parametrize("size", [(3840, 2160), (7680, 4320)])
+def test_full_size_frame_parity(size):
+    """BASELINE's 4K and 8K frames against the oracle: streaming passes over the whole frame (G-buffer and depth-moment chains
+    bit-exact on every level, light chains in tolerance), gather / denoise / swapchain on three 16-row strips (top, middle, bottom) —
+    the oracle's passes take the same row ranges, which keeps the CPU side to a few seconds."""
+    W, Hh = size
+    strips = ((0, 16), ((Hh // 2) & ~15, ((Hh // 2) & ~15) + 16), (Hh - 16, Hh))
+    sc, p, ref = H.oracle_frame_on_strips(0xC0FFEE, W, Hh, strips)
+    r = harness.Renderer(W, Hh)
+    r.upload_scene(sc)
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
+    r.sync()
+    H.check_big_frame(r.download_image, ref, strips, W, Hh, whole_frame_images=(W == 3840))
+    r.close()
