@@ -28,6 +28,8 @@ int orc_blur_level(const lgcu_blur_layer_builder_data *params, const lgcu_image 
 int orc_gi_gather(const lgcu_indirect_lighting_data *params, const lgcu_image *blurredDirectLight,
                   const lgcu_image *blurredDepthMoments, const lgcu_image *normal, const lgcu_image *depthStencil,
                   const lgcu_image *indirectLight, uint32_t flags, const lgcu_rows *rows);
+/* work counters (pixels, march samples, horizon hits) of the last orc_gi_gather call whose flags had bit 31 set */
+void orc_gi_gather_counters(unsigned long long out[3]);
 int orc_denoise(const lgcu_denoiser_data *params, const lgcu_image *noisy, const lgcu_image *normal,
                 const lgcu_image *depthMoments, const lgcu_image *denoised, const lgcu_rows *rows);
 int orc_final_gather(const lgcu_final_gatherer_data *params, const lgcu_image *directLight,

@@ -190,3 +190,36 @@ def test_big_frame_checker_on_the_oracle_itself():
     H.check_big_frame(lambda name: getattr(whole, name), ref, strips, W, Hh)
     # rows outside the strips were not computed by the strip oracle (poison), so the checker really only looks at the strips
     assert not np.array_equal(ref.indirectLight.level_bytes(0)[40:60], whole.indirectLight.level_bytes(0)[40:60])
+
+
+def test_gather_work_counters():
+    """orc_gi_gather's work counters (flag bit 31): march samples per pixel follow from the iteration-count formula alone
+    (indirectLighting.frag:202-214), so they can be cross-checked in numpy; hits are bounded by the samples."""
+    W, Hh = 250, 141
+    sc, p, ref = H.oracle_frame(12, W, Hh)
+    port = loader.port()
+    port.lib.orc_gi_gather_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+    out_img = images.HostImage(abi.FORMAT_R16G16B16A16_SFLOAT, W, Hh, 1)
+    v = lambda img: C.byref(img.view())
+    assert port.gi_gather(C.byref(p.indirect), v(ref.blurredDirectLight), v(ref.blurredDepthMoments), v(ref.normal), v(ref.depthStencil), v(out_img), 0x80000000, None) == 0
+    assert out_img.levels_equal(ref.indirectLight, 0)  # counting does not change the result
+    c = (C.c_ulonglong * 3)()
+    port.lib.orc_gi_gather_counters(c)
+    pixels, samples, hits = (int(x) for x in c)
+    assert pixels == W * Hh and 0 < hits < samples
+    # numpy restatement of BoxRayCast + iterationsCount in fp32
+    f = np.float32
+    x, y = np.meshgrid(np.arange(W, dtype=np.float32) + f(0.5), np.arange(Hh, dtype=np.float32) + f(0.5))
+    idx = (x.astype(np.int32) % 4) + (y.astype(np.int32) % 4) * 4
+    total = 0
+    for d in range(4):
+        ang = (f(1.57075) * (idx.astype(np.float32) / f(16.0))) + f(1.57075) * f(d)
+        dx, dy = np.cos(ang).astype(np.float32), np.sin(ang).astype(np.float32)
+        with np.errstate(divide="ignore"):
+            ivx, ivy = f(1.0) / dx, f(1.0) / dy
+        t1, t2, t3, t4 = (f(0.0) - x) * ivx, (f(W) - x) * ivx, (f(0.0) - y) * ivy, (f(Hh) - y) * ivy
+        path = np.abs(np.minimum(np.maximum(t1, t2), np.maximum(t3, t4))).astype(np.float32)
+        near = f(W) / f(1000.0)
+        its = (np.log(path / near).astype(np.float32) / f(0.944197714328765869140625)).astype(np.int32) + 1
+        total += int(np.maximum(its, 0).sum())
+    assert abs(total - samples) <= 0.002 * samples  # cosf/sinf/logf of numpy vs libm may move a boundary pixel by one step
