@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--no-present", action="store_true", help="strips: skip the composite of the swapchain strips on rank 0")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="strips: p2p = our copy/flag kernels over NVLink peer memory (CUDA IPC); nccl = torch.distributed send/recv per slab")
+    ap.add_argument("--strip-input", default="fragments", choices=["fragments", "mesh"],
+                    help="strips: what every rank starts from — its strip of the pre-rasterised fragment buffer (uploaded per frame in the e2e leg), or the "
+                         "mesh scene, which every rank rasterises for its own rows on the device (ShadowPass + GBufferRasterPass with lgcu_rows)")
     ap.add_argument("--balance", type=int, default=3, help="strips (p2p): up to this many measure -> rebalance rounds of the strip boundaries (0 = equal rows)")
     ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -453,17 +456,23 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     cls = multigpu.P2PStripRenderer if args.transport == "p2p" else multigpu.StripRenderer
     gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
 
+    mesh = scene.scene_mesh(seed) if args.strip_input == "mesh" else None
+
     def build(bounds):
         """Strip renderer for `bounds` with this rank's strip of the rasterised scene generated into pinned memory and uploaded."""
         y0, y1 = bounds[rank]
         frag_host = torch.empty((max(y1 - y0, 1), W * 32), dtype=torch.uint8).pin_memory()
         frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
-        scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
+        if mesh is None:
+            scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
         sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present, bounds=bounds)
         sr.renderer.upload_objects(objects.ctypes.data, len(objects))
         sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
         ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
-        sr.upload_strip(ptr, W * 32)
+        if args.strip_input == "mesh":
+            sr.renderer.upload_mesh(mesh)  # the front stage then rasterises this rank's rows itself
+        else:
+            sr.upload_strip(ptr, W * 32)
         return sr, frag_host, ptr
 
     def stage_profile(sr, frames=8):
@@ -530,7 +539,10 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         received = sr.received_bytes
 
         def e2e_step():
-            sr.upload_strip(full_view_ptr, W * 32)
+            if mesh is not None:
+                sr.renderer.upload_mesh(mesh)
+            else:
+                sr.upload_strip(full_view_ptr, W * 32)
             frame()
             if rank == 0:
                 sr.renderer.download_swapchain(swap_host.data_ptr(), W * 4)
@@ -551,13 +563,15 @@ def run_strips(args, rank: int, world: int, local_rank: int):
             "config": {
                 "workload": f"{W}x{H} full GI frame tile-sharded into {world} row strips with NVLink halo exchange (BASELINE configs[3])",
                 "pass_list": "fused stages: front | exchange | chains | exchange | gather + final | composite on rank 0",
-                "strips": bounds, "present": not args.no_present, "cuda_graph": use_graph,
+                "strips": bounds, "present": not args.no_present, "cuda_graph": use_graph, "strip_input": args.strip_input,
                 "transport": "own copy + flag kernels over NVLink peer memory (CUDA IPC)" if args.transport == "p2p" else "NCCL send/recv per slab",
                 "exchange_bytes_per_frame_all_ranks": int(recv_all.item()),
                 "l2": "inputs larger than L2 (per-GPU strip working set > 126 MB at 8K / 8 GPUs)",
             },
             "clocks": clocks,
-            "e2e": {"value": npx / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 32, "d2h_bytes_per_step": W * H * 4,
+            "e2e": {"value": npx / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "h2d_bytes_per_step": (W * H * 32) if mesh is None else world * sum(a.nbytes for a in (mesh.vertices, mesh.indices, mesh.draws, mesh.objects)),
+                    "d2h_bytes_per_step": W * H * 4,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": 6 * args.steps * world,
             "kernels_per_frame": 6,
