@@ -116,3 +116,13 @@ def test_missing_cuda_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(abi, "LIB_DIR", tmp_path)
     with pytest.raises(abi.LibraryMissing):
         abi.load_lgcu()
+
+
+def test_every_entry_point_is_documented():
+    """Every function include/lgcu.h declares is accounted for in INTEGRATION.md or DESIGN.md (which reference interface it replaces,
+    or why it has none)."""
+    hdr = (ROOT / "include" / "lgcu.h").read_text()
+    names = sorted(set(re.findall(r"\b(lgcu_[a-z0-9_]+)\s*\(", hdr)))
+    docs = (ROOT / "INTEGRATION.md").read_text() + (ROOT / "DESIGN.md").read_text()
+    missing = [n for n in names if n not in docs]
+    assert len(names) >= 30 and not missing, missing
