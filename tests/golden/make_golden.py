@@ -74,8 +74,51 @@ def aux_fixture() -> None:
     print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")
 
 
+def bundled_scene_fixture(W: int = 192, H: int = 108, shadow: int = 256) -> None:
+    """BASELINE configs[0], scaled down to fixture size: the reference's bundled sample scene (bin/data/Scenes/SponzaScene.json +
+    OBJ meshes, loaded where they lie by tests/bundled_scene.py), rasterised by the oracle's rasteriser (rule R) from the
+    application's default camera / light, then through the reference's own SPIR-V passes. Same layout as the ssvgi_* fixtures."""
+    import ctypes as C
+
+    from legitengine_b200 import raster
+    from tests import bundled_scene as B
+
+    mesh = B.load_bundled_scene()
+    m = scene.frame_matrices(W, H)
+    port, ms = loader.port(), raster.host_mesh_desc(mesh)
+    frags = np.zeros((H, W), dtype=abi.FRAGMENT_DTYPE)
+    g = abi.GBufferBuilderData(abi.mat4(m.view), abi.mat4(m.proj), 0.0, 0.0)
+    assert port.raster_gbuffer(C.byref(g), C.byref(ms), W, H, frags.ctypes.data, frags.strides[0], None) == 0
+    depth = np.zeros((shadow, shadow), dtype=np.float32)
+    sp = abi.ShadowmapBuilderData(abi.mat4(m.light_view), abi.mat4(m.light_proj))
+    assert port.raster_shadow_map(C.byref(sp), C.byref(ms), shadow, depth.ctypes.data, depth.strides[0]) == 0
+    sc = scene.Scene(W, H, 0, m, frags, mesh.objects, depth)
+    p = passes.make_params(W, H, m, 0)
+    fi = passes.FrameImages(W, H, images.HostImage, shadow_size=shadow)
+    passes.run_pass_list(loader.ref(), fi, p, passes.upload_inputs(fi, sc))
+    out = {
+        "meta": np.array([0, W, H, 0, 0, shadow], dtype=np.int64),
+        "triangles": np.array([mesh.triangle_count], dtype=np.int64),
+        "fragments": frags.view(np.uint8).reshape(H, W * 32).copy(),
+        "objects": mesh.objects.view(np.uint8).reshape(-1).copy(),
+        "shadow_map": depth.copy(),
+        "view": m.view, "proj": m.proj, "light_view": m.light_view, "light_proj": m.light_proj,
+    }
+    for iname, img in fi.items():
+        if iname == "shadowMap":
+            continue
+        for l in range(img.mips):
+            w, h = img.level_size(l)
+            if w > 0 and h > 0:
+                out[f"img.{iname}.{l}"] = np.ascontiguousarray(img.level_bytes(l))
+    path = HERE / f"bundled_sponza_{W}x{H}.npz"
+    np.savez_compressed(path, **out)
+    print(f"{path.name}: {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main() -> None:
     aux_fixture()
+    bundled_scene_fixture()
     ref = loader.ref()
     for name, (seed, W, H, boxes, radius, shadow) in FIXTURES.items():
         sc = scene.make_scene(seed, W, H, n_boxes=boxes, shadow_size=shadow)

@@ -82,6 +82,9 @@ GOLDEN_DIR = __import__("pathlib").Path(__file__).resolve().parent / "golden"
 GOLDEN_NAMES = sorted(p.stem for p in GOLDEN_DIR.glob("ssvgi_*.npz"))
 
 
+BUNDLED_GOLDEN = "bundled_sponza_192x108"  # the reference's bundled sample scene (BASELINE configs[0]) at fixture size
+
+
 def load_golden(name: str):
     """-> (scene, params, FrameImages on the host holding the reference arm's outputs, denoise radius)."""
     z = np.load(GOLDEN_DIR / f"{name}.npz")

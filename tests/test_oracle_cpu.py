@@ -223,3 +223,43 @@ def test_gather_work_counters():
         its = (np.log(path / near).astype(np.float32) / f(0.944197714328765869140625)).astype(np.int32) + 1
         total += int(np.maximum(its, 0).sum())
     assert abs(total - samples) <= 0.002 * samples  # cosf/sinf/logf of numpy vs libm may move a boundary pixel by one step
+
+
+def test_port_reproduces_the_bundled_scene_fixture():
+    """tests/golden/bundled_sponza_192x108.npz: the reference's bundled sample scene (BASELINE configs[0]: SponzaScene.json, 466k
+    triangles) rasterised by the oracle's rasteriser and shaded by the reference's own SPIR-V passes. The port must reproduce every
+    image and level bit for bit from the fixture's inputs."""
+    sc, p, want, _ = H.load_golden(H.BUNDLED_GOLDEN)
+    got = _run(loader.port(), sc, p, sc.width, sc.height, want.shadow_size)
+    levels = passes.mip_levels_built(sc.width, sc.height)
+    for iname, img, l in _all_levels(want):
+        if iname == "shadowMap" or (l >= levels and iname in ("directLight", "depthMoments")):
+            continue
+        assert getattr(got, iname).levels_equal(img, l), f"{iname} level {l} differs from the bundled-scene fixture"
+    # it really is the bundled scene: both emissive hornbugs and the atrium are in view, and every pixel is covered
+    ids = sc.fragments["objectId"]
+    assert set(np.unique(ids).tolist()) == {0, 1, 4} and (ids != abi.LGCU_NO_OBJECT).all()
+
+
+@pytest.mark.skipif(not __import__("tests.bundled_scene", fromlist=["available"]).available(), reason="needs the reference's bundled scene under /root/reference")
+def test_bundled_scene_fixture_regenerates_from_the_reference_assets():
+    """Loader (tests/bundled_scene.py: Scene.h / Mesh.h semantics) + oracle rasteriser reproduce the fixture's fragment buffer, object
+    table and shadow map from the OBJ / JSON files where they lie."""
+    from legitengine_b200 import raster
+    from tests import bundled_scene as B
+
+    z = np.load(H.GOLDEN_DIR / f"{H.BUNDLED_GOLDEN}.npz")
+    _, W, Hh, _, _, shadow = (int(v) for v in z["meta"])
+    mesh = B.load_bundled_scene()
+    assert mesh.triangle_count == int(z["triangles"][0]) and len(mesh.draws) == 5
+    assert np.array_equal(mesh.objects.view(np.uint8).reshape(-1), z["objects"])
+    m = scene.frame_matrices(W, Hh)
+    port, ms = loader.port(), raster.host_mesh_desc(mesh)
+    frags = np.zeros((Hh, W), dtype=abi.FRAGMENT_DTYPE)
+    g = abi.GBufferBuilderData(abi.mat4(m.view), abi.mat4(m.proj), 0.0, 0.0)
+    assert port.raster_gbuffer(C.byref(g), C.byref(ms), W, Hh, frags.ctypes.data, frags.strides[0], None) == 0
+    assert np.array_equal(frags.view(np.uint8).reshape(Hh, W * 32), z["fragments"])
+    depth = np.zeros((shadow, shadow), dtype=np.float32)
+    sp = abi.ShadowmapBuilderData(abi.mat4(m.light_view), abi.mat4(m.light_proj))
+    assert port.raster_shadow_map(C.byref(sp), C.byref(ms), shadow, depth.ctypes.data, depth.strides[0]) == 0
+    assert np.array_equal(depth.view(np.uint32), z["shadow_map"].view(np.uint32))
