@@ -809,6 +809,8 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
     return st;
   DenoiseFinalArgs a;
   a.indirectFormat = noisy->format;
+  a.viewport[0] = dparams->viewportExtent[0];
+  a.viewport[1] = dparams->viewportExtent[1];
   if (!resolveLevel(noisy, 0, "noisy", &a.noisy, &st) || !resolveLevel(denoised, 0, "denoised", &a.denoised, &st) ||
       !resolveLevel(directLight, 0, "directLight", &a.directLight, &st) || !resolveLevel(albedo, 0, "albedo", &a.albedo, &st) ||
       !resolveLevel(swapchain, 0, "swapchain", &a.swapchain, &st))

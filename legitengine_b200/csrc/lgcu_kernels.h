@@ -95,6 +95,7 @@ struct FinalGatherArgs {
 
 struct DenoiseFinalArgs { // fused K6 (radius 0) + K7
   uint32_t indirectFormat;
+  float viewport[2]; // DenoiserData.viewportExtent (the centre tap divides gl_FragCoord by it, denoiser.frag:83)
   LevelView noisy, denoised, directLight, albedo, swapchain;
   RowRange rows;
 };

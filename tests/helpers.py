@@ -145,41 +145,150 @@ def oracle_frame_on_strips(seed: int, width: int, height: int, strips):
     return sc, p, fi
 
 
-def rows_close(got: images.HostImage, want: images.HostImage, y0: int, y1: int, what: str, max_outside_frac: float = 1e-3, min_psnr: float = 60.0, level: int = 0):
-    """assert_close restricted to rows [y0, y1) of one level (north-star tolerance: 1e-3 or one fp16 ulp of the value, PSNR >= 60 dB)."""
-    a, b = got.level_f32(level)[y0:y1], want.level_f32(level)[y0:y1]
-    tol = np.maximum(1e-3, F16_EPS * np.abs(b))
-    outside = float((np.abs(a - b) > tol).any(axis=2).mean())
-    assert outside <= max_outside_frac, f"{what} rows [{y0},{y1}): {outside:.2e} of the texels outside the tolerance"
-    # PSNR against a peak of at least 1.0: a dark strip must not turn the 60 dB bar into something stricter than max-abs 1e-3
-    peak = max(1.0, float(np.max(np.abs(b))))
-    assert psnr(a, b, peak) >= min_psnr, f"{what} rows [{y0},{y1}): PSNR {psnr(a, b, peak):.1f} dB"
+# ---- THE parity bar for radiance (one bar for every gather / frame test) ---------------------------------------------------------
+# A texel is an outlier if any channel differs by more than max(1e-3, one fp16 ulp of the reference value). A comparison passes with
+# at most OUTLIER_BAR of the texels outside and PSNR >= 60 dB (peak >= 1). Every comparison feeds the CUDA pass and the oracle the
+# SAME inputs (chained frames are re-based stage by stage, `stagewise_check`), so nothing compounds and nothing needs a looser bar.
+#
+# One physical exception, measured not assumed: at 4K / 8K the reference's gather is dominated, near bright emitters, by its OWN fp32
+# rounding noise (tangent = normalize(normalize(a) - normalize(b)) of two rays 2.5e-4 rad apart, P = cam + ray * z rounded at |P|, then
+# P - C): the reference differs from the exact value of its own formula (oracle/gather_noise_probe.c: same inputs, same discrete
+# decisions, binary64 arithmetic) on 2e-3 of the texels of the 4K mid rows and 2e-2 at 8K (max-abs 11.6). No evaluation order other
+# than the shader's own can agree with it there. So when `exact` is given the bar is applied against BOTH:
+#   * the kernel against the exact value: the plain bar (OUTLIER_BAR), and
+#   * the kernel against the fp32 reference: at most OUTLIER_BAR + 1.5 x the reference's own outlier fraction against the exact value
+#     (triangle inequality), PSNR >= 60 dB.
+# The binary64 evaluation also marks the texels where the formula itself is DISCONTINUOUS (a horizon angle within 1e-3 rad of atan's
+# branch cut at +-pi: `h < maxH` then flips for every later sample under a 1-ulp perturbation, and the fp32 shader and the binary64
+# evaluation land on different sides — up to 11.6 in radiance at 8K); they are reported and left out (< 1e-3 of the texels).
+# The shader-order kernel (LGCU_GI_STRICT) reproduces the reference's rounding and is held to the plain bar at every size.
+OUTLIER_BAR = 1e-4
+_REPORT = GOLDEN_DIR.parent.parent / "gpurun_out" / "parity_report.jsonl"
 
 
-def check_big_frame(get_image, ref: passes.FrameImages, strips, width: int, height: int, whole_frame_images=True):
-    """Parity of a full-size frame: `get_image(name)` returns the device frame's HostImage. G-buffer and the depth-moment chains are
-    bit-exact over the whole frame (every level); the light chains within tolerance; gather / denoise / swapchain on `strips`."""
-    levels = passes.mip_levels_built(width, height)
+def _outliers(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    d = np.abs(a - b)
+    finite = np.isfinite(a) & np.isfinite(b)
+    d = np.where(finite, d, np.where(np.isnan(a) == np.isnan(b), 0.0, np.inf))
+    return (d > np.maximum(1e-3, F16_EPS * np.abs(b))).any(axis=-1)
+
+
+def radiance_report(got: np.ndarray, want: np.ndarray, what: str, exact=None) -> Dict[str, float]:
+    """got / want: float arrays (..., channels); exact: None or (binary64 values, branch-cut mask) from `exact_gather`. Returns (and logs
+    to gpurun_out/parity_report.jsonl) the outlier fraction, max-abs, 99.99th percentile and PSNR, over the texels outside the mask."""
+    keep = np.ones(got.shape[:-1], dtype=bool) if exact is None else ~exact[1]
+    g, w = got[keep], want[keep]
+    d = np.abs(g.astype(np.float64) - w.astype(np.float64))
+    d = np.where(np.isfinite(d), d, 0.0)
+    rep = {"what": what, "texels": int(keep.sum()), "outside": float(_outliers(g, w).mean()), "max_abs": float(d.max()),
+           "p9999": float(np.quantile(d.max(axis=-1), 0.9999)), "psnr": float(psnr(g, w, max(1.0, float(np.max(np.abs(w))))))}
+    if exact is not None:
+        e = exact[0][keep]
+        rep["branch_cut_texels"] = float((~keep).mean())  # texels where the reference's formula is discontinuous (left out)
+        rep["reference_outside_exact"] = float(_outliers(w, e).mean())  # the reference's own fp32 noise floor
+        rep["outside_exact"] = float(_outliers(g, e).mean())
+    if _REPORT.parent.is_dir():
+        import json
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps(rep) + "\n")
+    return rep
+
+
+def assert_radiance(got: np.ndarray, want: np.ndarray, what: str, exact=None) -> Dict[str, float]:
+    rep = radiance_report(got, want, what, exact)
+    if exact is None:
+        assert rep["outside"] <= OUTLIER_BAR, rep
+    else:
+        floor = rep["reference_outside_exact"]
+        assert rep["branch_cut_texels"] <= 2e-3 or rep["texels"] < 20000, rep  # (tiny fixtures: a handful of texels is already more)
+        assert rep["outside_exact"] <= OUTLIER_BAR, rep
+        assert rep["outside"] <= OUTLIER_BAR + 1.5 * floor, rep
+    assert rep["psnr"] >= 60.0, rep
+    return rep
+
+
+def assert_images_radiance(got: images.HostImage, want: images.HostImage, what: str, level: int = 0, rows=None, exact=None):
+    a, b = got.level_f32(level), want.level_f32(level)
+    if rows is not None:
+        a, b = a[rows[0]:rows[1]], b[rows[0]:rows[1]]
+    return assert_radiance(a[..., :3], b[..., :3], f"{what} level {level}" + (f" rows {list(rows)}" if rows is not None else ""), exact)
+
+
+def exact_gather(p: passes.FrameParams, fi: passes.FrameImages, rows):
+    """The gather in binary64 on the images of `fi` (oracle/gather_noise_probe.c; frame constants and the centre position as the
+    fp32 shader computes them), rows [y0, y1): ((y1 - y0, W, 3) float32 rounded to the target format like a render-target store,
+    (y1 - y0, W) bool mask of the texels with a horizon angle on atan's branch cut, where the formula is discontinuous)."""
+    lib = loader.port().lib
+    lib.orc_gi_gather_f64.restype = C.c_int
+    y0, y1 = rows
+    out = np.zeros((y1 - y0, fi.width, 3), dtype=np.float32)
+    cut = np.zeros((y1 - y0, fi.width), dtype=np.uint8)
+    v = lambda img: C.byref(img.view(0, None))
+    st = lib.orc_gi_gather_f64(C.byref(p.indirect), v(fi.blurredDirectLight), v(fi.blurredDepthMoments), v(fi.normal), v(fi.depthStencil),
+                               out.ctypes.data_as(C.c_void_p), C.c_uint64(fi.width * 3), C.byref(abi.LgcuRows(y0, y1)), C.c_uint32(3),
+                               cut.ctypes.data_as(C.c_void_p), C.c_uint64(fi.width))
+    assert st == 0
+    if fi.indirect_format == abi.FORMAT_R16G16B16A16_SFLOAT:
+        out = out.astype(np.float16).astype(np.float32)
+    return out, cut.astype(bool)
+
+
+def stagewise_check(get_image, p: passes.FrameParams, ref: passes.FrameImages, strips=None, exact: bool = True, whole_frame_images: bool = True,
+                    gbuffer_bit_exact=("normal", "depthStencil"), what: str = "frame"):
+    """Parity of a CHAINED frame, one pass at a time: every stage of the device frame (`get_image(name)` -> HostImage) is compared with
+    the oracle's pass run on the DEVICE frame's own inputs for that stage, so each pass meets the one bar by itself:
+      G-buffer bit-exact (albedo / emissive: pow(colour, 2.2) within the bar), depth-moment chains bit-exact on every level,
+      direct light within the bar, the light mip and blur chains BIT-EXACT given the device's level 0,
+      gather within the bar (against the binary64 evaluation as well when `exact`), denoise (r = 0) a copy, swapchain +-1 code.
+    `strips`: row ranges for gather / denoise / composite (big frames); None = whole frame."""
+    W, Hh = ref.width, ref.height
+    be = loader.port()
+    levels = passes.mip_levels_built(W, Hh)
+    v = lambda img, base=0, n=None: C.byref(img.view(base, n))
+    dev = passes.FrameImages(W, Hh, images.HostImage, indirect_format=ref.indirect_format, shadow_size=ref.shadow_size)  # device outputs, on the host
+    reb = passes.FrameImages(W, Hh, images.HostImage, indirect_format=ref.indirect_format, shadow_size=ref.shadow_size)  # oracle passes on them
+    fetch = lambda name: setattr(dev, name, get_image(name)) or getattr(dev, name)
+    for name in ("normal", "depthStencil", "albedo", "emissive", "depthMoments", "blurredDepthMoments", "directLight", "blurredDirectLight"):
+        fetch(name)
+    dev.shadowMap = ref.shadowMap
     if whole_frame_images:
-        for name in ("normal", "depthStencil"):
-            assert_bit_exact(get_image(name), getattr(ref, name), 0, name)
-        for name in ("albedo", "emissive"):  # pow(colour, 2.2) per object: libm vs device pow, then fp16 rounding (as in test_gbuffer_resolve)
-            r = compare_level(get_image(name), getattr(ref, name), 0)
+        for name in gbuffer_bit_exact:
+            assert_bit_exact(dev.__dict__[name], getattr(ref, name), 0, name)
+        for name in ("albedo", "emissive"):
+            r = compare_level(getattr(dev, name), getattr(ref, name), 0)
             assert r["outside_tol"] == 0 and r["mismatched_texels"] <= 0.02 * r["texels"], (name, r)
         for name in ("depthMoments", "blurredDepthMoments"):
-            got = get_image(name)
             for l in range(levels):
-                assert_bit_exact(got, getattr(ref, name), l, name)
-        for name in ("directLight", "blurredDirectLight"):
-            got = get_image(name)
-            for l in range(levels):
-                w, h = images.mip_size(width, height, l)
-                if w * h >= 4096:  # one texel of a tiny level is already more than the allowed fraction
-                    rows_close(got, getattr(ref, name), 0, h, f"{name} level {l}", level=l)
-    indirect, denoised, swap = get_image("indirectLight"), get_image("denoisedIndirectLight"), get_image("swapchain")
-    for y0, y1 in strips:
-        rows_close(indirect, ref.indirectLight, y0, y1, "indirectLight")
-        rows_close(denoised, ref.denoisedIndirectLight, y0, y1, "denoisedIndirectLight")
-        a = swap.level_raw(0)[y0:y1].astype(np.int32)
-        b = ref.swapchain.level_raw(0)[y0:y1].astype(np.int32)
-        assert (np.abs(a - b) > 1).mean() < 1e-3, f"swapchain rows [{y0},{y1})"
+                assert_bit_exact(getattr(dev, name), getattr(ref, name), l, name)
+        # K2 on the device's own G-buffer
+        assert be.direct_light(C.byref(p.light), v(dev.albedo), v(dev.emissive), v(dev.normal), v(dev.depthStencil), v(dev.shadowMap), v(reb.directLight, 0, 1), None) == 0
+        assert_images_radiance(dev.directLight, reb.directLight, f"{what}: directLight")
+        # K3 / K4 on the device's own level 0: exact-order fp32 + RTNE fp16 stores -> bit-exact
+        reb.directLight.level_bytes(0)[...] = dev.directLight.level_bytes(0)
+        for l in range(1, levels):
+            assert be.mip_level(C.byref(p.mip), v(reb.directLight, l - 1, 1), v(reb.directLight, l, 1), None) == 0
+            assert_bit_exact(dev.directLight, reb.directLight, l, "directLight mips (re-based)")
+        for l in range(levels):
+            w, h = images.mip_size(W, Hh, l)
+            bp = abi.BlurLayerBuilderData((C.c_int32 * 4)(w, h, 0, 0), 0 if l == 0 else 2)
+            assert be.blur_level(C.byref(bp), v(reb.directLight, l, 1), v(reb.blurredDirectLight, l, 1), None) == 0
+            assert_bit_exact(dev.blurredDirectLight, reb.blurredDirectLight, l, "blurredDirectLight (re-based)")
+    for name in ("indirectLight", "denoisedIndirectLight", "swapchain"):
+        fetch(name)
+    for rows in (strips if strips is not None else ((0, Hh),)):
+        r = C.byref(abi.LgcuRows(*rows))
+        # K5 on the device's pyramids
+        assert be.gi_gather(C.byref(p.indirect), v(dev.blurredDirectLight), v(dev.blurredDepthMoments), v(dev.normal), v(dev.depthStencil), v(reb.indirectLight), 0, r) == 0
+        ex = exact_gather(p, dev, rows) if exact else None
+        assert_images_radiance(dev.indirectLight, reb.indirectLight, f"{what}: indirectLight", rows=rows, exact=ex)
+        # K6 (r = 0) on the device's indirect light: a copy up to the centre-tap blend of SURVEY.md Appendix B
+        assert be.denoise(C.byref(p.denoiser), v(dev.indirectLight), v(dev.normal), v(dev.depthMoments), v(reb.denoisedIndirectLight), r) == 0
+        # (the shader's centre tap blends up to 2^-24 * W of a neighbouring texel in on the ~3 % of columns / rows where
+        # fl(fl((x + .5) / W) * W) != x + .5; the kernels load the texel itself: same bar)
+        assert_images_radiance(dev.denoisedIndirectLight, reb.denoisedIndirectLight, f"{what}: denoisedIndirectLight", rows=rows)
+        # K7 on the device's images
+        assert be.final_gather(C.byref(p.final), v(dev.directLight), v(dev.blurredDirectLight), v(dev.albedo), v(dev.denoisedIndirectLight), v(reb.swapchain), r) == 0
+        a = dev.swapchain.level_raw(0)[rows[0]:rows[1]].astype(np.int32)
+        b = reb.swapchain.level_raw(0)[rows[0]:rows[1]].astype(np.int32)
+        assert np.abs(a - b).max() <= 1, f"{what}: swapchain rows {rows}: {np.abs(a - b).max()} codes"
+    return dev, reb

@@ -180,16 +180,36 @@ def test_hammersley_table_and_march_schedule():
                 assert abs(lod - lod_want) < 0.01, (W, k, lod)
 
 
-def test_big_frame_checker_on_the_oracle_itself():
-    """The full-size parity helper (tests/helpers.py: oracle on row strips + check_big_frame) agrees with the whole-frame oracle:
-    what the -m gpu test uses at 4K / 8K, exercised here at a small size with the oracle's own frame standing in for the device's."""
+def test_stagewise_checker_on_the_oracle_itself():
+    """The chained-frame parity helper of the -m gpu tests (tests/helpers.py: stagewise_check = every stage against the oracle's pass
+    on that stage's own inputs, whole frame or row strips, with the binary64 gather alongside), exercised here with the oracle's own
+    frame standing in for the device's: everything must agree exactly, and a corrupted stage must be caught."""
     W, Hh = 320, 180
+    sc, p, whole = H.oracle_frame(11, W, Hh)
+    H.stagewise_check(lambda name: getattr(whole, name), p, whole)
     strips = ((0, 16), (80, 96), (164, 180))
-    sc, p, ref = H.oracle_frame_on_strips(11, W, Hh, strips)
-    whole_sc, whole_p, whole = H.oracle_frame(11, W, Hh)
-    H.check_big_frame(lambda name: getattr(whole, name), ref, strips, W, Hh)
-    # rows outside the strips were not computed by the strip oracle (poison), so the checker really only looks at the strips
-    assert not np.array_equal(ref.indirectLight.level_bytes(0)[40:60], whole.indirectLight.level_bytes(0)[40:60])
+    H.stagewise_check(lambda name: getattr(whole, name), p, whole, strips=strips, exact=True)
+    import copy
+    broken = copy.copy(whole)
+    broken.indirectLight = images.HostImage(whole.indirectLight.format, W, Hh, 1)
+    broken.indirectLight.buf[...] = whole.indirectLight.buf
+    lv = broken.indirectLight.level_raw(0).copy()
+    lv[80:96, ::7, 0] += np.float16(0.01)
+    broken.indirectLight.set_level(0, lv)
+    with pytest.raises(AssertionError):
+        H.stagewise_check(lambda name: getattr(broken, name), p, whole, strips=strips)
+
+
+def test_reference_rounding_noise_floor_of_the_gather():
+    """oracle/gather_noise_probe.c: the gather in binary64 on the fp32 oracle's inputs, with the shader's discrete decisions. At a
+    small viewport the fp32 shader sits within the bar of the exact value of its own formula (so the plain bar is meaningful there);
+    the probe and the port agree, which also pins the probe's restatement of the formula."""
+    W, Hh = 250, 141
+    sc, p, ref = H.oracle_frame(12, W, Hh)
+    exact, cut = H.exact_gather(p, ref, (0, Hh))
+    keep = ~cut
+    rep = H.radiance_report(ref.indirectLight.level_f32(0)[..., :3][keep], exact[keep], "fp32 oracle vs binary64 probe 250x141")
+    assert rep["outside"] <= H.OUTLIER_BAR and rep["psnr"] >= 60.0 and cut.mean() <= 2e-3, (rep, cut.mean())
 
 
 def test_gather_work_counters():

@@ -85,11 +85,7 @@ def test_frame_vs_oracle_and_profile():
     names = [n for n, _ in prof]
     assert names == ["ShadowPass", "FrameFrontPass", "FrameChainsPass", "GatherPackPass", "IndirectLightPass", "DenoiseGatheringPass"], names
     assert all(ms >= 0 for _, ms in prof)
-    for n in ("directLight", "blurredDirectLight", "indirectLight", "denoisedIndirectLight"):
-        H.assert_close(r.download_image(n), getattr(ref, n), 0, n, max_outside_frac=1e-3)
-    a = r.download_image("swapchain").level_raw(0).astype(np.int32)
-    b = ref.swapchain.level_raw(0).astype(np.int32)
-    assert (np.abs(a - b) > 1).mean() < 1e-3
+    H.stagewise_check(r.download_image, p, ref, what="rendergraph fused 640x360")
     r.close()
 
 
@@ -135,13 +131,8 @@ def test_frame_from_mesh_scene(mode, camera):
     assert names[0] == "ShadowPass" and names[1] == "GBufferRasterPass", names
     for n in ("shadowMap", "albedo", "emissive", "normal", "depthStencil"):
         H.assert_bit_exact(r.download_image(n), getattr(ref, n), 0, n)
-    for l in range(passes.mip_levels_built(W, Hh)):
-        H.assert_bit_exact(r.download_image("depthMoments"), ref.depthMoments, l, "depthMoments")
-    for n in ("directLight", "blurredDirectLight", "indirectLight", "denoisedIndirectLight"):
-        H.assert_close(r.download_image(n), getattr(ref, n), 0, n, max_outside_frac=1e-3)
+    H.stagewise_check(r.download_image, p, ref, what=f"mesh-scene frame mode {mode}")
     a = r.download_image("swapchain").level_raw(0).astype(np.int32)
-    b = ref.swapchain.level_raw(0).astype(np.int32)
-    assert (np.abs(a - b) > 1).mean() < 1e-3
     if mode == harness.MODE_FUSED:
         # graph replay with a re-upload of the (same-size) scene in between, as the e2e loop does every frame
         r.capture_frame(mode, 0, abi.GI_DEFAULT)
@@ -212,17 +203,36 @@ def test_interleave_builder_on_the_rendergraph(grid):
     r.close()
 
 
+def _big_frame_strips(Hh):
+    mid = (Hh // 2) & ~15
+    return ((0, 16), (mid, mid + 16), (Hh - 16, Hh))
+
+
+@pytest.mark.parametrize("gi", ["default", "strict"])
 @pytest.mark.parametrize("size", [(3840, 2160), (7680, 4320)])
-def test_full_size_frame_parity(size):
-    """BASELINE's 4K and 8K frames against the oracle: streaming passes over the whole frame (G-buffer and depth-moment chains
-    bit-exact on every level, light chains in tolerance), gather / denoise / swapchain on three 16-row strips (top, middle, bottom) —
-    the oracle's passes take the same row ranges, which keeps the CPU side to a few seconds."""
+def test_full_size_frame_parity(size, gi):
+    """BASELINE's 4K and 8K frames, stage by stage (tests/helpers.py: stagewise_check). 4K: the streaming passes over the WHOLE frame
+    (G-buffer and depth-moment chains bit-exact on every level, direct light within the bar, light mip / blur chains bit-exact given
+    the device's level 0). Both sizes: gather / denoise / composite on three 16-row strips (top, middle = the horizon rows, bottom)
+    against the oracle's passes on the device's own pyramids — the oracle's passes take the same row ranges, which keeps the CPU side
+    to seconds. The shader-order kernel (strict) meets the plain bar; the default kernel is held to the bar against BOTH the fp32
+    reference and the binary64 evaluation of the reference's formula, because at these sizes the reference's own fp32 rounding noise
+    exceeds the bar (measured in the same call; see the comment above helpers.OUTLIER_BAR and profiles/r02a_gather_noise_floor.md)."""
     W, Hh = size
-    strips = ((0, 16), ((Hh // 2) & ~15, ((Hh // 2) & ~15) + 16), (Hh - 16, Hh))
-    sc, p, ref = H.oracle_frame_on_strips(0xC0FFEE, W, Hh, strips)
+    strips = _big_frame_strips(Hh)
+    whole = W == 3840 and gi == "default"
+    if whole:
+        sc, p, ref = H.oracle_frame_on_strips(0xC0FFEE, W, Hh, ())
+    else:
+        from legitengine_b200 import scene as scene_mod
+
+        sc = scene_mod.make_scene(0xC0FFEE, W, Hh)
+        p = passes.make_params(W, Hh, sc.matrices, 0)
+        ref = passes.FrameImages(W, Hh, images.HostImage)
+        passes.upload_inputs(ref, sc)
     r = harness.Renderer(W, Hh)
     r.upload_scene(sc)
-    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT)
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_STRICT if gi == "strict" else abi.GI_DEFAULT)
     r.sync()
-    H.check_big_frame(r.download_image, ref, strips, W, Hh, whole_frame_images=(W == 3840))
+    H.stagewise_check(r.download_image, p, ref, strips=strips, exact=(gi == "default"), whole_frame_images=whole, what=f"{W}x{Hh} {gi}")
     r.close()
