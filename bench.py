@@ -12,7 +12,9 @@ One "step" = one frame of the workload through the C++ rendergraph harness (libl
           (ShadowPass + GBufferRasterPass), renders the frame and copies the BGRA8 swapchain image device->host, all inside the
           timed region. value_from_mesh is the same frame with the scene resident. e2e_fragments is the other host-buffer form:
           the pre-rasterised 32 B/px fragment buffer uploaded every step (PCIe-bound).
-N > 1   : one process per GPU (torchrun); independent frames per GPU (BASELINE configs[4], "weak"), no data-path collective
+N > 1   : one process per GPU (torchrun). Default: BASELINE configs[3] — ONE 7680x4320 frame cut into row strips with NVLink halo
+          exchange ("strong"); the line also carries the same run's single-GPU 8K frame time (`single_gpu`) and the throughput mode
+          of configs[4] (`replicas`: independent 4K frames per GPU, no data-path collective). --shard replicas makes that the line.
 --impl reference : the reference's own SPIR-V passes on the host cores (oracle/_ref, else the C port), bounded sample.
 The CPU oracle is used here ONLY for the cpu_baseline / reference legs — never on the product path.
 """
@@ -50,14 +52,14 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", default="4k")
+    ap.add_argument("--workload", default=None, help="4k | 8k | 1080p | 512 | WxH (default: 4k on one GPU, 8k for the strip-sharded frame on N > 1)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="fused", choices=["fused", "passes"])
     ap.add_argument("--strict", action="store_true", help="use the shader-order parity gather kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 60))")
     ap.add_argument("--frames-in-flight", type=int, default=3, help="e2e leg: frames in flight (renderer + stream + pinned swapchain per slot)")
-    ap.add_argument("--shard", default="replicas", choices=["replicas", "strips"],
+    ap.add_argument("--shard", default=None, choices=["replicas", "strips"],
                     help="N > 1: replicas = independent frames per GPU (weak scaling, BASELINE configs[4]); strips = ONE frame cut into row strips "
                          "with NVLink halo exchange (strong scaling, BASELINE configs[3])")
     ap.add_argument("--no-present", action="store_true", help="strips: skip the composite of the swapchain strips on rank 0")
@@ -72,6 +74,7 @@ def parse_args():
 
 
 def workload_size(name: str):
+    name = name or "4k"
     if name in WORKLOADS:
         return WORKLOADS[name]
     w, h = name.lower().split("x")
@@ -147,6 +150,8 @@ def cpu_frame_seconds(width: int, height: int, frames: int, warmup: int = 1):
     from oracle import loader
 
     be = loader.ref() if loader.have_ref() else loader.port()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    be.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     sc = scene.make_scene(0xC0FFEE, width, height)
     p = passes.make_params(width, height, sc.matrices, 0)
     fi = passes.FrameImages(width, height, images.HostImage)
@@ -164,16 +169,19 @@ def cpu_frame_seconds(width: int, height: int, frames: int, warmup: int = 1):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    W, H = workload_size(args.workload)
-    sw, sh = max(W // 4, 64), max(H // 4, 36)  # bounded sample: 1/16 of the pixels per step
+    shard = args.shard or ("strips" if world > 1 else "replicas")
+    W, H = workload_size(args.workload or ("8k" if (world > 1 and shard == "strips") else "4k"))  # the workload of our arm's line at this N
+    div = 4 if W * H <= 3840 * 2160 else 8  # bounded sample: 960x540 per step at 4K and 8K (~0.2 s on 16 cores)
+    sw, sh = max(W // div, 64), max(H // div, 36)
     kind, cores, times = cpu_frame_seconds(sw, sh, args.steps, min(args.warmup, 1))
     sec = float(np.mean(times))
     value = sw * sh / sec / 1e6
-    sample = f"{sw}x{sh} full frame (1/16 of the {W}x{H} pixels) per step, same synthetic scene generator, all passes K1..K7"
+    sample = f"{sw}x{sh} full frame (1/{div * div} of the {W}x{H} pixels) per step, same synthetic scene generator, all passes K1..K7"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W}x{H} full GI frame (BASELINE configs[2] + G-buffer resolve), CPU sample: {sample}",
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if (world > 1 and shard == "strips") else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W}x{H} full GI frame, CPU sample: {sample}",
                    "what": "reference SPIR-V passes (spirv-cross C++ backend + glm) on host cores" if kind == "reference" else "plain-C port of the reference shaders on host cores"},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -203,9 +211,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     mode = harness.MODE_FUSED if args.mode == "fused" else harness.MODE_PASS_GRANULAR
     gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
 
-    # synthetic rasterised scene (seed differs per rank: independent frames), generated on the host into pinned memory
+    # synthetic rasterised scene, generated on the host into pinned memory. Every rank renders the SAME scene: the gather's cost depends
+    # on what the frame shows, and with different scenes the MAX over ranks would measure the scenes, not the GPUs
     m = scene.frame_matrices(W, H)
-    seed = 0xC0FFEE + rank
+    seed = 0xC0FFEE
     frag_host = torch.empty((H, W * 32), dtype=torch.uint8).pin_memory()
     frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(H, W)
     scene.scene_fragments(seed, W, H, m, out=frags)
@@ -433,6 +442,41 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+
+def resident_frame_ms(W: int, H: int, seed: int, steps: int, warmup: int = 5, gi_flags: int = 0):
+    """ms per frame of the fused W x H frame on THIS rank's GPU with the rasterised scene resident (CUDA-graph replay, CUDA events)."""
+    import torch
+
+    from legitengine_b200 import abi, harness, scene
+
+    m = scene.frame_matrices(W, H)
+    frags = np.empty((H, W), dtype=abi.FRAGMENT_DTYPE)
+    scene.scene_fragments(seed, W, H, m, out=frags)
+    objects = scene.scene_objects(seed)
+    shadow = scene.scene_shadow_map(seed, m)
+    stream = torch.cuda.Stream()
+    r = harness.Renderer(W, H, stream=stream.cuda_stream)
+    r.upload_fragments(frags.ctypes.data, frags.strides[0])
+    r.upload_objects(objects.ctypes.data, len(objects))
+    r.upload_light_depth(np.ascontiguousarray(shadow).ctypes.data, 1024)
+    r.sync()
+    r.render_frame(harness.MODE_FUSED, 0, gi_flags)
+    r.sync()
+    r.capture_frame(harness.MODE_FUSED, 0, gi_flags)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            r.replay_frame()
+        e0.record(stream)
+        for _ in range(steps):
+            r.replay_frame()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    r.close()
+    return ms
+
+
 def run_strips(args, rank: int, world: int, local_rank: int):
     """ONE frame of the workload cut into row strips over the ranks (legitengine_b200/multigpu.py): per step every rank renders
     its strip in stages with halo exchanges over NCCL/NVLink in between, then the swapchain strips are composited on rank 0."""
@@ -553,6 +597,18 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(recv_all)
         # per-rank, per-stage GPU time of un-captured frames (events between the stages on every rank): shows where a strip waits
         stage_ms = stage_profile(sr) if args.transport == "p2p" else None
+    # --- the same run's single-GPU frame of this workload (rank 0 alone; the others wait), and BASELINE configs[4]'s throughput mode:
+    # every GPU renders independent 4K frames (same scene on every rank, so that the MAX over ranks measures the GPUs, not the scenes)
+    extra_steps = max(10, min(args.steps, 50))
+    torch.cuda.synchronize()
+    dist.barrier()
+    single_ms = resident_frame_ms(W, H, seed, extra_steps, gi_flags=gi_flags) if rank == 0 else 0.0
+    dist.barrier()
+    rw, rh = WORKLOADS["4k"]
+    rep = torch.tensor([resident_frame_ms(rw, rh, seed, extra_steps, gi_flags=gi_flags)], device="cuda")
+    rep_all = [torch.zeros_like(rep) for _ in range(world)]
+    dist.all_gather(rep_all, rep)
+    rep_ms = [float(t.item()) for t in rep_all]
     if rank == 0:
         npx = W * H
         peak, peak_src = measured_peak_gbs()
@@ -575,6 +631,12 @@ def run_strips(args, rank: int, world: int, local_rank: int):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": 6 * args.steps * world,
             "kernels_per_frame": 6,
+            "single_gpu": {"ms_per_step": single_ms, "value": npx / (single_ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": extra_steps,
+                           "speedup_of_this_line": single_ms / ms_per_step,
+                           "note": f"the whole {W}x{H} frame on rank 0's GPU alone, measured in this run after the strip-sharded leg"},
+            "replicas": {"value": world * rw * rh / (max(rep_ms) * 1e-3) / 1e6, "unit": "Mpix/s", "scaling": "weak", "ms_per_step_per_rank": [round(v, 4) for v in rep_ms],
+                         "frames_per_s": world / (max(rep_ms) * 1e-3), "steps": extra_steps,
+                         "note": f"BASELINE configs[4] throughput mode: every GPU renders independent {rw}x{rh} frames, no data-path collective; MAX over ranks"},
             "stage_ms_per_rank": stage_ms,
             "balance": balance_log,
             "roofline_frame": {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
@@ -614,9 +676,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world > 1 and args.shard == "strips":
+    shard = args.shard or ("strips" if world > 1 else "replicas")
+    if world > 1 and shard == "strips":
+        args.workload = args.workload or "8k"
         run_strips(args, rank, world, local_rank)
         return
+    args.workload = args.workload or "4k"
     run_ours(args, rank, world, local_rank)
 
 

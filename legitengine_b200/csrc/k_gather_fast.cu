@@ -1,32 +1,40 @@
 // k_gather_fast.cu — screen-space GI gather (K5), throughput variant for sm_100a.
 //
 // Same function as SH/SSVGI/indirectLighting.frag:114-272 (k_gather_strict.cu is the line-by-line form). The pass is bound by
-// FP32 issue slots and the LSU, not by HBM (≈25 trilinear pyramid samples per pixel), so the design removes
-// instructions and load requests, not bytes:
+// instruction issue, not by HBM (≈25 trilinear pyramid samples and ≈8 trilinear light fetches per pixel; ncu r01j: issue slots 75 %
+// busy, DRAM 12 %), so the design removes instructions, not bytes:
 //
 //  * Pattern-coherent CTAs. The shader's 4x4 interleaved pattern gives every pixel with the same (x&3, y&3) the same march
 //    directions, step offsets and LODs. A CTA owns a 64x64 (or 64x32) pixel tile and walks pattern classes in a CTA-uniform
-//    loop; in each pass thread t shades pixel (4*(t&15) + ox, 4*(t>>4) + oy). Direction, step offset, LOD and mip geometry are
-//    therefore uniform-datapath operands, every level branch is uniform, and neighbouring lanes read neighbouring texels
-//    from LOD 2 upwards. The passes of a CTA re-touch the same pyramid neighbourhood, which stays in L1; the 16 classes of a
-//    tile are split over 4 CTAs that sit next to each other in the grid (finer work units for the tail of the grid, shared L2
-//    footprint: measured DRAM traffic of the launch = 1.18x its algorithmic bytes).
+//    loop; in each pass thread t shades one pixel of the class. Direction, step offset, LOD and mip geometry are therefore
+//    uniform-datapath operands, every level branch is uniform, and neighbouring lanes read neighbouring texels from LOD 2 upwards.
+//    The 16 classes of a tile are split over 4 CTAs that sit next to each other in the grid (finer work units for the tail of
+//    the grid, shared L2 footprint: measured DRAM traffic of the launch = 1.18x its algorithmic bytes).
 //  * No transcendental per sample: pow/log (step offset, LOD, iteration count) come from host tables shared with the strict
 //    kernel (bit-identical level selection). The per-sample unprojection collapses to FMAs: the ray through pixel s is
 //    R(s) = Ra*sx + Rb*sy + Rc (affine in pixel coordinates), so along a march direction every dot product of the horizon test
 //    is affine in the step offset with per-direction constants.
-//  * One 16-byte load per bilinear depth footprint: the march reads the quad-packed side pyramid built by packDepthQuads
-//    (per level (w+1)x(h+1) float4 = the four clamp-to-edge .r taps of the footprint whose top-left texel is (qx-1, qy-1)),
-//    so the per-sample address math is one clamp + one magic-number floor per axis and there are 2 loads per trilinear
-//    sample instead of 8. Without a scratch buffer (lgcu_gi_gather) the same kernel fetches the four taps individually.
-//  * Hits are processed inline (they are spatially coherent: a warp runs the hit body on ≈2.7 of its ≈6.4 march steps per
-//    direction with ≈70 % of the lanes active; compacting them buys nothing). A sample is rejected with a half-plane +
-//    cross-product test instead of atan; on a hit atan2 is an 8-term minimax polynomial (1.2e-7 rad) and sin(2h)/cos(2h)
-//    of ComputeHorizonContribution come algebraically from the horizon vector: cos2h = (x²-y²)/(x²+y²), sin2h = 2xy/(x²+y²).
-//    The light fetch reuses the footprint (integer taps + weights) of the depth fetch.
-//  * What is numerically delicate is kept in the shader's order: the centre position is reconstructed from the D32 depth
-//    exactly as the shader does (its fp32 cancellation noise is part of the reference result and is amplified by
-//    1/sample distance), so the two variants see the same centre.
+//  * The step rows of a pass's pattern class are staged in shared memory (112 bytes per step): five 16-byte broadcast loads per march
+//    step replace ~20 uniform-datapath loads, address computations and UR->R moves (ncu r02e: 31 % of the executed instructions were
+//    such overhead). Marching two or four directions of a pixel in lock-step was measured and dropped: it needs 80 / 128 registers,
+//    and this kernel lives on occupancy (4 -> 3 -> 2 resident CTAs per SM: 1.49 -> 1.69 -> 1.93 ms; lock-step 2 / 4: 1.81 / 2.25 ms).
+//  * Private side pyramid (lgcu_gi_gather_pack, built once per frame from the two blurred pyramids):
+//      - depth, levels >= 1: per level (w+1)x(h+1) float4 = the four clamp-to-edge .r taps of the bilinear footprint whose top-left
+//        texel is (qx-1, qy-1) -> ONE 16-byte load per footprint, no clamps, one address;
+//      - light, levels >= 2: the same footprint as 12 floats (4 taps x RGB, already converted to fp32) -> three 16-byte loads, no
+//        clamps, no fp16->fp32 converts (24 per trilinear fetch in the plain layout, 15 % of the stall samples in r01b). Levels >= 2
+//        hold 1/12 of the pyramid's texels, so this costs 33 MB at 4K; levels 0 and 1 (touched by the first two march steps only)
+//        are read from the images themselves (level 0 of the depth pyramid as well: packing it was 3/4 of the pack pass).
+//    Without a scratch buffer (lgcu_gi_gather) the same kernel fetches every tap from the images.
+//  * Hits are processed inline (they are spatially coherent). A sample is rejected with a half-plane + cross-product test instead of
+//    atan; on a hit atan2 is an 8-term minimax polynomial (1.2e-7 rad) and sin(2h)/cos(2h) of ComputeHorizonContribution come
+//    algebraically from the horizon vector: cos2h = (x²-y²)/(x²+y²), sin2h = 2xy/(x²+y²). The light fetch reuses the footprint
+//    (integer taps + weights) of the depth fetch.
+//  * What is numerically delicate is kept in the shader's order: the centre position is reconstructed from the D32 depth exactly
+//    as the shader does (its fp32 cancellation noise is part of the reference result and is amplified by 1/sample distance), so
+//    the two variants see the same centre. Everything after that is evaluated in cancellation-free forms: against the binary64
+//    evaluation of the shader's formula (oracle/gather_noise_probe.c) this kernel has < 1e-4 outliers at 4K and 8K, where the fp32
+//    shader itself has 2e-3 / 2e-2 (tests/helpers.py: OUTLIER_BAR).
 #include <cmath>
 #include <cstdlib>
 
@@ -39,23 +47,28 @@ namespace {
 constexpr int kTile = 64;      // pixels per tile edge
 constexpr int kThreads = 256;  // 16x16 pixels of one pattern class per pass
 constexpr int kMaxSteps = 12;  // march steps the tables hold (8 are reached for landscape viewports at any resolution)
+constexpr int kDepthQuadLevel0 = 0, kLightQuadLevel0 = 2; // first levels of the side pyramid's depth / light quads
 constexpr uint32_t F16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, D32 = LGCU_FORMAT_D32_SFLOAT;
 constexpr float kFloorMagic = 12582912.0f; // 1.5 * 2^23: x + magic (rounded down) has floor(x) in its low mantissa bits
 constexpr int kFloorMagicBits = 0x4B400000;
 
-struct __align__(16) LevelGeom { // per pyramid level
+// Per pyramid level, three 16-byte groups (the kernel reads them as float4 / int4 from shared memory)
+struct __align__(16) LevelGeom {
   float scaleX, scaleY; // w_l / viewport.x, h_l / viewport.y
   float maxX, maxY;     // w_l - 1, h_l - 1
-  int quadOfs, quadPitch; // level origin and row pitch of the quad-packed depth pyramid, in float4
+  int quadOfs, quadPitch; // depth quads: level origin and row pitch in float4
+  int lightOfs;           // light quads: level origin in float4, three per entry, same pitch (levels >= kLightQuadLevel0)
+  int mode;               // bit 0: depth quads present, bit 1: light quads present
   int texOfs, texPitch;   // level origin and row pitch in 8-byte texels (both pyramids share the layout)
   int wm1, hm1;
-  int pad0, pad1;
 };
-struct __align__(16) StepRow { // per (pattern, step): everything the march needs for one sample, in one uniform 112-byte row
+struct __align__(16) StepRow { // per (pattern, step): everything the march needs for one sample, in one 112-byte row = 7 x 16 bytes
   float off, frac;
   int l0, l1;
   LevelGeom g0, g1;
 };
+constexpr int kRowVecs = sizeof(StepRow) / 16;
+static_assert(sizeof(StepRow) == 112 && kRowVecs == 7, "StepRow layout");
 struct __align__(16) DirEntry { // per (pattern, direction)
   float dirX, dirY, invDirX, invDirY;
   float rdX, rdY, rdZ, q2; // Rd = Ra*dirX + Rb*dirY, q2 = |Rd|²
@@ -108,9 +121,9 @@ struct Footprint {
   int ix, iy;
   float a, b;
 };
-__device__ __forceinline__ Footprint footprint(const LevelGeom &g, float sx, float sy) {
+__device__ __forceinline__ Footprint footprint(const float4 g /* scaleX, scaleY, maxX, maxY */, float sx, float sy) {
   Footprint f;
-  const float u = fminf(fmaxf(fmaf(sx, g.scaleX, -0.5f), -1.0f), g.maxX), v = fminf(fmaxf(fmaf(sy, g.scaleY, -0.5f), -1.0f), g.maxY);
+  const float u = fminf(fmaxf(fmaf(sx, g.x, -0.5f), -1.0f), g.z), v = fminf(fmaxf(fmaf(sy, g.y, -0.5f), -1.0f), g.w);
   const float tu = __fadd_rd(u, kFloorMagic), tv = __fadd_rd(v, kFloorMagic);
   f.a = u - (tu - kFloorMagic);
   f.b = v - (tv - kFloorMagic);
@@ -119,29 +132,45 @@ __device__ __forceinline__ Footprint footprint(const LevelGeom &g, float sx, flo
   return f;
 }
 
-template <bool kQuads>
-__device__ __forceinline__ float fetchDepth(const LevelGeom &g, const Footprint &f, const float4 *__restrict__ quads, const float2 *__restrict__ moments) {
+struct Pyramids {
+  const float2 *__restrict__ moments; // blurredDepthMoments, level 0 base
+  const uint2 *__restrict__ light;    // blurredDirectLight, level 0 base
+  const float4 *__restrict__ side;    // side pyramid (depth quads, then light quads) or nullptr
+};
+
+// q = {quadOfs, quadPitch, lightOfs, mode}, tex = {texOfs, texPitch, wm1, hm1} of the level (the latter only read without quads)
+template <bool kSide> __device__ __forceinline__ float fetchDepth(const int4 q, const uint4 *texRow, const Footprint &f, const Pyramids &p) {
   float t00, t10, t01, t11;
-  if (kQuads) {
-    const float4 q = __ldg(quads + (unsigned)(g.quadOfs + (f.iy + 1) * g.quadPitch + (f.ix + 1)));
-    t00 = q.x, t10 = q.y, t01 = q.z, t11 = q.w;
+  if (kSide) {
+    const float4 v = __ldg(p.side + (unsigned)(q.x + (f.iy + 1) * q.y + (f.ix + 1)));
+    t00 = v.x, t10 = v.y, t01 = v.z, t11 = v.w;
   } else {
-    const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, g.wm1), y0 = max(f.iy, 0), y1 = min(f.iy + 1, g.hm1);
-    const unsigned r0 = g.texOfs + y0 * g.texPitch, r1 = g.texOfs + y1 * g.texPitch;
-    t00 = __ldg(&moments[r0 + x0].x), t10 = __ldg(&moments[r0 + x1].x), t01 = __ldg(&moments[r1 + x0].x), t11 = __ldg(&moments[r1 + x1].x);
+    const uint4 tex = *texRow;
+    const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, (int)tex.z), y0 = max(f.iy, 0), y1 = min(f.iy + 1, (int)tex.w);
+    const unsigned r0 = tex.x + y0 * tex.y, r1 = tex.x + y1 * tex.y;
+    t00 = __ldg(&p.moments[r0 + x0].x), t10 = __ldg(&p.moments[r0 + x1].x), t01 = __ldg(&p.moments[r1 + x0].x), t11 = __ldg(&p.moments[r1 + x1].x);
   }
   return lerpf(lerpf(t00, t10, f.a), lerpf(t01, t11, f.a), f.b);
 }
 
-__device__ __forceinline__ float3 fetchLight(const LevelGeom &g, const Footprint &f, const uint2 *__restrict__ light) {
-  const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, g.wm1), y0 = max(f.iy, 0), y1 = min(f.iy + 1, g.hm1);
-  const unsigned o0 = g.texOfs + y0 * g.texPitch, o1 = g.texOfs + y1 * g.texPitch;
-  const uint2 r00 = __ldg(&light[o0 + x0]), r10 = __ldg(&light[o0 + x1]), r01 = __ldg(&light[o1 + x0]), r11 = __ldg(&light[o1 + x1]);
+__device__ __forceinline__ float3 fetchLight(const int4 q, const uint4 *texRow, const Footprint &f, const Pyramids &p) {
+  float3 r;
+  if (q.w & 2) { // same for every thread of the CTA: 12 fp32 values {t00.rgb, t10.rgb, t01.rgb, t11.rgb} in three 16-byte loads
+    const float4 *e = p.side + (unsigned)(q.z + 3 * ((f.iy + 1) * q.y + (f.ix + 1)));
+    const float4 A = __ldg(e), B = __ldg(e + 1), C = __ldg(e + 2);
+    r.x = lerpf(lerpf(A.x, A.w, f.a), lerpf(B.z, C.y, f.a), f.b);
+    r.y = lerpf(lerpf(A.y, B.x, f.a), lerpf(B.w, C.z, f.a), f.b);
+    r.z = lerpf(lerpf(A.z, B.y, f.a), lerpf(C.x, C.w, f.a), f.b);
+    return r;
+  }
+  const uint4 tex = *texRow;
+  const int x0 = max(f.ix, 0), x1 = min(f.ix + 1, (int)tex.z), y0 = max(f.iy, 0), y1 = min(f.iy + 1, (int)tex.w);
+  const unsigned o0 = tex.x + y0 * tex.y, o1 = tex.x + y1 * tex.y;
+  const uint2 r00 = __ldg(&p.light[o0 + x0]), r10 = __ldg(&p.light[o0 + x1]), r01 = __ldg(&p.light[o1 + x0]), r11 = __ldg(&p.light[o1 + x1]);
   const float2 a00 = __half22float2(*reinterpret_cast<const __half2 *>(&r00.x)), a10 = __half22float2(*reinterpret_cast<const __half2 *>(&r10.x));
   const float2 a01 = __half22float2(*reinterpret_cast<const __half2 *>(&r01.x)), a11 = __half22float2(*reinterpret_cast<const __half2 *>(&r11.x));
   const float b00 = __low2float(*reinterpret_cast<const __half2 *>(&r00.y)), b10 = __low2float(*reinterpret_cast<const __half2 *>(&r10.y));
   const float b01 = __low2float(*reinterpret_cast<const __half2 *>(&r01.y)), b11 = __low2float(*reinterpret_cast<const __half2 *>(&r11.y));
-  float3 r;
   r.x = lerpf(lerpf(a00.x, a10.x, f.a), lerpf(a01.x, a11.x, f.a), f.b);
   r.y = lerpf(lerpf(a00.y, a10.y, f.a), lerpf(a01.y, a11.y, f.a), f.b);
   r.z = lerpf(lerpf(b00, b10, f.a), lerpf(b01, b11, f.a), f.b);
@@ -161,25 +190,37 @@ __device__ __forceinline__ float dot3Exact(V3 a, V3 b) { return __fadd_rn(__fadd
 
 // kT = threads per CTA: a CTA shades a 64 x (kT / 4) pixel tile (256 -> 64x64, 128 -> 64x32). The smaller tile doubles the CTA count
 // for row strips and small frames, where the grid would otherwise be a couple of waves with a long tail (multi-GPU strips).
-template <bool kQuads, int kMinBlocks, int kT>
+// kSide: the side pyramid exists (depth quads on every level, light quads from level kLightQuadLevel0 up).
+// The step rows of the pass's pattern class are staged in shared memory once per pass (7 x 16 bytes per step): the march loop reads
+// them with five 16-byte broadcast loads instead of ~20 uniform-datapath loads, address computations and UR->R moves.
+template <bool kSide, int kMinBlocks, int kT, bool kCompactWarp>
 __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
-                                                                          const float4 *__restrict__ quads, int xSlices) {
+                                                                          const float4 *__restrict__ side, int xSlices) {
+  __shared__ uint4 sRow[kMaxSteps * kRowVecs];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
   // The 16 pattern classes of a tile are split over xSlices CTAs (0 or 1 = one CTA does all 16) that are neighbours in blockIdx.x
   const int nSlices = xSlices > 0 ? xSlices : 1, slice = (int)blockIdx.x % nSlices;
   const int tileX = ((int)blockIdx.x / nSlices) * kTile, tileY = (a.rows.y0 & ~3) + blockIdx.y * (kT / 4);
   const float vpx = a.viewport[0], vpy = a.viewport[1];
-  const float invVpx = 1.0f / vpx, invVpy = 1.0f / vpy;
+  const float invVpx10 = 10.0f / vpx, invVpy10 = 10.0f / vpy;
   const V3 cam = v3(a.cam[0], a.cam[1], a.cam[2]);
   const V3 Ra = v3(tb.ra[0], tb.ra[1], tb.ra[2]), Rb = v3(tb.rb[0], tb.rb[1], tb.rb[2]), Rc = v3(tb.rc[0], tb.rc[1], tb.rc[2]);
-  const float2 *__restrict__ moments = reinterpret_cast<const float2 *>(a.moments.lv[0].ptr);
-  const uint2 *__restrict__ light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
-  const int tx = 4 * (t & 15), ty = 4 * (t >> 4);
+  Pyramids pyr;
+  pyr.moments = reinterpret_cast<const float2 *>(a.moments.lv[0].ptr);
+  pyr.light = reinterpret_cast<const uint2 *>(a.light.lv[0].ptr);
+  pyr.side = side;
+  // lanes of a warp: 16 x 2 pixels of the class (64 x 8 px) or, compact, 8 x 4 (32 x 16 px)
+  const int tx = kCompactWarp ? 4 * ((((t >> 5) & 1) << 3) + (t & 7)) : 4 * (t & 15);
+  const int ty = kCompactWarp ? 4 * (((t >> 6) << 2) + ((t >> 3) & 3)) : 4 * (t >> 4);
+  const int maxSteps = tb.maxSteps;
 
   const int idxPerCta = 16 / nSlices, idx0 = slice * idxPerCta;
 #pragma unroll 1
   for (int idx = idx0; idx < idx0 + idxPerCta; idx++) { // one pattern class per pass (CTA-uniform)
+    __syncthreads(); // the previous pass is done with the staged rows
+    for (int v = t; v < maxSteps * kRowVecs; v += kT) sRow[v] = reinterpret_cast<const uint4 *>(&tb.row[idx * kMaxSteps])[v];
+    __syncthreads();
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
     if (!__any_sync(0xffffffffu, active)) continue;
@@ -202,14 +243,15 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const float n0 = sqrtf(q0);
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
     float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
-    const StepRow *__restrict__ rows = &tb.row[idx * kMaxSteps];
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
       const DirEntry de = tb.dir[idx][d];
       const V3 Rd = v3(de.rdX, de.rdY, de.rdZ);
       // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
-      const float q2 = de.q2, q1 = 2.0f * dotf(R0, Rd);
+      float q2;
+      asm("mov.f32 %0, %1;" : "=f"(q2) : "f"(de.q2)); // opaque: keeps q2 in a register (the compiler otherwise re-reads it from the constant bank every march step)
+      const float q1 = 2.0f * dotf(R0, Rd);
       const float n1 = sqrtf(q0 + q1 + q2);
       const float g = (q1 + q2) * fastRcp(n0 + n1);
       const V3 tanU = v3(fmaf(Rd.x, n0, -R0.x * g), fmaf(Rd.y, n0, -R0.y * g), fmaf(Rd.z, n0, -R0.z * g));
@@ -229,7 +271,11 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
       const float path = fabsf(glmMin(glmMax(t1, t2), glmMax(t3, t4)));
       int iterations = 0;
 #pragma unroll
-      for (int n = 0; n < kMaxSteps; n++) iterations += (path >= tb.iterThreshold[n]) ? 1 : 0; // thresholds beyond maxSteps are +inf
+      for (int n = 0; n < 8; n++) iterations += (path >= tb.iterThreshold[n]) ? 1 : 0; // thresholds beyond maxSteps are +inf
+      if (maxSteps > 8) { // uniform; not reached by landscape viewports
+#pragma unroll 1
+        for (int n = 8; n < maxSteps; n++) iterations += (path >= tb.iterThreshold[n]) ? 1 : 0;
+      }
       if (!active) iterations = 0;
       // ambient term 0.01 * HC(0, maxH) (:209): cos(0) = 1, sin(0) = 0.  L = sum(Ls*c) - 0.01*sum(c) + 0.01*hc0
       float Lx = 0.0f, Ly = 0.0f, Lz = 0.0f;
@@ -237,13 +283,28 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
       // per-direction affine coefficients of the horizon vector
       const float yE = dotf(tang, E), yR0 = tb.raySign * dotf(tang, R0);
       const float xRd = tb.raySign * dotf(eye, Rd), yRd = tb.raySign * dotf(tang, Rd);
+      const float dirX = de.dirX, dirY = de.dirY;
 
       const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
-      // horizon test + hit body of one march sample whose depth z is known (:241-263)
-      auto shade = [&](int k, const StepRow &st, const Footprint &f0, const Footprint &f1, float z) {
-        const float zs = z * fastRsqrt(fmaf(st.off, fmaf(st.off, q2, q1), q0)); // z / |R(s)|
-        const float hx = fmaf(zs, fmaf(st.off, xRd, xR0), xE); // dot(eye, P - C)      :241-252
-        const float hy = fmaf(zs, fmaf(st.off, yRd, yR0), yE); // dot(tangent, P - C)
+      const uint4 *row = sRow;
+#pragma unroll 1
+      for (int k = 0; k < warpIters; k++, row += kRowVecs) { // :214
+        const float4 hdr = *reinterpret_cast<const float4 *>(row); // off, frac, l0, l1
+        const float off = hdr.x, frac = hdr.y;
+        const float sx = fmaf(dirX, off, px), sy = fmaf(dirY, off, py); // :218-219 (in pixels)
+        const int4 qa = *reinterpret_cast<const int4 *>(row + 2);
+        const Footprint f0 = footprint(*reinterpret_cast<const float4 *>(row + 1), sx, sy);
+        float z = fetchDepth<kSide>(qa, row + 3, f0, pyr);
+        Footprint f1; // only set and only read when tri
+        const bool tri = frac > 0.0f; // the same for every thread of the CTA
+        if (tri) {
+          f1 = footprint(*reinterpret_cast<const float4 *>(row + 4), sx, sy);
+          z = fmaf(frac, fetchDepth<kSide>(*reinterpret_cast<const int4 *>(row + 5), row + 6, f1, pyr) - z, z); // :240
+        }
+        // horizon test + hit body (:241-263)
+        const float zs = z * fastRsqrt(fmaf(off, fmaf(off, q2, q1), q0)); // z / |R(s)|
+        const float hx = fmaf(zs, fmaf(off, xRd, xR0), xE); // dot(eye, P - C)      :241-252
+        const float hy = fmaf(zs, fmaf(off, yRd, yR0), yE); // dot(tangent, P - C)
         // h < maxH for angles in (-pi, pi]: different half planes decide directly, otherwise the cross product does
         const bool lower = hy < 0.0f, lowerM = my < 0.0f;
         const bool hit = (lower != lowerM) ? lower : (hx * my - hy * mx > 0.0f);
@@ -252,41 +313,27 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           const float inv = fastRcp(fmaxf(fmaf(hx, hx, hy * hy), 1e-37f));
           const float c2 = (hx * hx - hy * hy) * inv, s2 = 2.0f * hx * hy * inv;
           const float hc = eN4 * (c2 - c2m) + tN4 * (((2.0f * maxH - 2.0f * h) - s2m) + s2); // :44-49
-          const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-          const float su = sx * invVpx, sv = sy * invVpy;
-          // product of the four saturates of :220-228 (at most one per axis is below 1)
-          const float side = saturatef(fminf(su, 1.0f - su) * 10.0f) * saturatef(fminf(sv, 1.0f - sv) * 10.0f);
-          float3 ls = fetchLight(st.g0, f0, light); // :256
-          if (st.frac > 0.0f) {
-            const float3 hi = fetchLight(st.g1, f1, light);
-            ls.x = fmaf(st.frac, hi.x - ls.x, ls.x);
-            ls.y = fmaf(st.frac, hi.y - ls.y, ls.y);
-            ls.z = fmaf(st.frac, hi.z - ls.z, ls.z);
+          // product of the four saturates of :220-228 (at most one per axis is below 1): sat(min(u, 1 - u) * 10)
+          const float ex = fminf(sx, vpx - sx) * invVpx10, ey = fminf(sy, vpy - sy) * invVpy10;
+          const float sideMult = saturatef(ex) * saturatef(ey);
+          float3 ls = fetchLight(qa, row + 3, f0, pyr); // :256
+          if (tri) {
+            const float3 hi = fetchLight(*reinterpret_cast<const int4 *>(row + 5), row + 6, f1, pyr);
+            ls.x = fmaf(frac, hi.x - ls.x, ls.x);
+            ls.y = fmaf(frac, hi.y - ls.y, ls.y);
+            ls.z = fmaf(frac, hi.z - ls.z, ls.z);
           }
-          const float c = hc * side; // :258
-          Lx = fmaf(ls.x, c, Lx);    // :261
+          const float c = hc * sideMult; // :258
+          Lx = fmaf(ls.x, c, Lx);        // :261
           Ly = fmaf(ls.y, c, Ly);
           Lz = fmaf(ls.z, c, Lz);
-          cSum += c;                 // :262
-          maxH = h;                  // :263
+          cSum += c;                     // :262
+          maxH = h;                      // :263
           c2m = c2;
           s2m = s2;
           mx = hx;
           my = hy;
         }
-      };
-#pragma unroll 1
-      for (int k = 0; k < warpIters; k++) { // :214
-        const StepRow &st = rows[k];
-        const float sx = fmaf(de.dirX, st.off, px), sy = fmaf(de.dirY, st.off, py); // :218-219 (in pixels)
-        const Footprint f0 = footprint(st.g0, sx, sy);
-        Footprint f1 = f0;
-        float z = fetchDepth<kQuads>(st.g0, f0, quads, moments);
-        if (st.frac > 0.0f) { // uniform branch
-          f1 = footprint(st.g1, sx, sy);
-          z = fmaf(st.frac, fetchDepth<kQuads>(st.g1, f1, quads, moments) - z, z); // :240
-        }
-        shade(k, st, f0, f1, z);
       }
       const float amb = -0.01f * cSum;
       sumX = fmaf(0.5f, Lx + amb, sumX); // :268
@@ -297,27 +344,40 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
   }
 }
 
-// Quad-packed depth pyramid: entry (qx, qy) of level l, qx in [0, w], qy in [0, h], holds the .r taps
-// {(x0,y0), (x1,y0), (x0,y1), (x1,y1)} with x0 = clamp(qx-1), x1 = clamp(qx), y0 = clamp(qy-1), y1 = clamp(qy).
+// Side pyramid. Entry (qx, qy) of level l, qx in [0, w], qy in [0, h], describes the bilinear footprint whose taps are
+// {(x0,y0), (x1,y0), (x0,y1), (x1,y1)} with x0 = clamp(qx-1), x1 = clamp(qx), y0 = clamp(qy-1), y1 = clamp(qy):
+// depth quads hold the four .r taps of blurredDepthMoments, light quads the four RGB taps of blurredDirectLight as fp32.
+constexpr int kMaxPackJobs = 2 * kMaxGatherLevels;
 struct PackArgs {
-  PyramidView moments;
-  int quadOfs[kMaxGatherLevels], quadPitch[kMaxGatherLevels], quadRows[kMaxGatherLevels];
-  int rowBegin[kMaxGatherLevels], rowEnd[kMaxGatherLevels]; // quad rows to (re)build per level
-  int blockBegin[kMaxGatherLevels + 1];                      // first CTA of each level (32x8 quads per CTA)
-  int levels;
+  PyramidView moments, light;
+  int jobLevel[kMaxPackJobs], jobLight[kMaxPackJobs];       // level, 0 = depth quads / 1 = light quads
+  int jobOfs[kMaxPackJobs], jobPitch[kMaxPackJobs];         // destination origin (float4) and entries per row
+  int jobRowBegin[kMaxPackJobs], jobRowEnd[kMaxPackJobs];   // entry rows to (re)build
+  int jobBlockBegin[kMaxPackJobs + 1];                      // first CTA of each job (32x8 entries per CTA)
+  int jobs;
 };
 
-__global__ void __launch_bounds__(256) packDepthQuadsKernel(const __grid_constant__ PackArgs p, float4 *__restrict__ quads) {
-  int l = 0;
-  while (l + 1 < p.levels && (int)blockIdx.x >= p.blockBegin[l + 1]) l++;
-  const LevelView lv = p.moments.lv[l];
-  const int bx = (p.quadPitch[l] + 31) / 32;
-  const int b = blockIdx.x - p.blockBegin[l];
-  const int qx = (b % bx) * 32 + (threadIdx.x & 31), qy = p.rowBegin[l] + (b / bx) * 8 + (threadIdx.x >> 5);
-  if (qx >= p.quadPitch[l] || qy >= p.rowEnd[l]) return;
-  const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
-  const float *r0 = reinterpret_cast<const float *>(lv.ptr + (size_t)y0 * lv.pitch), *r1 = reinterpret_cast<const float *>(lv.ptr + (size_t)y1 * lv.pitch);
-  quads[(size_t)p.quadOfs[l] + (size_t)qy * p.quadPitch[l] + qx] = make_float4(__ldg(r0 + 2 * x0), __ldg(r0 + 2 * x1), __ldg(r1 + 2 * x0), __ldg(r1 + 2 * x1));
+__global__ void __launch_bounds__(256) packSidePyramidKernel(const __grid_constant__ PackArgs p, float4 *__restrict__ side) {
+  int j = 0;
+  while (j + 1 < p.jobs && (int)blockIdx.x >= p.jobBlockBegin[j + 1]) j++;
+  const int l = p.jobLevel[j], pitch = p.jobPitch[j];
+  const int bx = (pitch + 31) / 32, b = blockIdx.x - p.jobBlockBegin[j];
+  const int qx = (b % bx) * 32 + (threadIdx.x & 31), qy = p.jobRowBegin[j] + (b / bx) * 8 + (threadIdx.x >> 5);
+  if (qx >= pitch || qy >= p.jobRowEnd[j]) return;
+  if (!p.jobLight[j]) {
+    const LevelView lv = p.moments.lv[l];
+    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
+    const float *r0 = reinterpret_cast<const float *>(lv.ptr + (size_t)y0 * lv.pitch), *r1 = reinterpret_cast<const float *>(lv.ptr + (size_t)y1 * lv.pitch);
+    side[(size_t)p.jobOfs[j] + (size_t)qy * pitch + qx] = make_float4(__ldg(r0 + 2 * x0), __ldg(r0 + 2 * x1), __ldg(r1 + 2 * x0), __ldg(r1 + 2 * x1));
+  } else {
+    const LevelView lv = p.light.lv[l];
+    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
+    const float4 t00 = Texel<F16>::load(lv, x0, y0), t10 = Texel<F16>::load(lv, x1, y0), t01 = Texel<F16>::load(lv, x0, y1), t11 = Texel<F16>::load(lv, x1, y1);
+    float4 *dst = side + (size_t)p.jobOfs[j] + 3 * ((size_t)qy * pitch + qx);
+    dst[0] = make_float4(t00.x, t00.y, t00.z, t10.x);
+    dst[1] = make_float4(t10.y, t10.z, t01.x, t01.y);
+    dst[2] = make_float4(t01.z, t11.x, t11.y, t11.z);
+  }
 }
 
 // Host: derive the fast tables. Returns false if the projection is not of the form the affine ray model assumes
@@ -390,10 +450,10 @@ bool buildFastTables(const GatherArgs &a, const GatherTables &t, FastTables *f) 
 }
 
 // Level geometry of the march rows and of the packer. Returns false if the two pyramids do not share one layout.
-bool buildLevelGeometry(const GatherArgs &a, FastTables *f, PackArgs *p) {
+// Side pyramid layout: depth quads of levels kDepthQuadLevel0.., then light quads (three float4 per entry) of levels kLightQuadLevel0..
+bool buildLevelGeometry(const GatherArgs &a, bool withSide, LevelGeom *geom, long long *sideFloat4s) {
   const double vpx = a.viewport[0], vpy = a.viewport[1];
-  LevelGeom geom[kMaxGatherLevels];
-  long long quadOfs = 0;
+  long long ofs = 0;
   for (int l = 0; l < a.moments.count; l++) {
     LevelGeom &g = geom[l];
     const LevelView &mv = a.moments.lv[l], &lv = a.light.lv[l];
@@ -409,86 +469,112 @@ bool buildLevelGeometry(const GatherArgs &a, FastTables *f, PackArgs *p) {
     g.texPitch = int(mv.pitch / 8);
     g.wm1 = mv.w - 1;
     g.hm1 = mv.h - 1;
-    g.quadOfs = int(quadOfs);
     g.quadPitch = mv.w + 1;
-    g.pad0 = g.pad1 = 0;
-    if (p) {
-      p->quadOfs[l] = g.quadOfs;
-      p->quadPitch[l] = g.quadPitch;
-      p->quadRows[l] = mv.h + 1;
+    g.quadOfs = 0;
+    g.lightOfs = 0;
+    g.mode = 0;
+    if (withSide && l >= kDepthQuadLevel0) {
+      g.quadOfs = int(ofs);
+      g.mode |= 1;
+      ofs += (long long)(mv.w + 1) * (mv.h + 1);
     }
-    quadOfs += (long long)(mv.w + 1) * (mv.h + 1);
-    if (quadOfs > 0x7fffffffLL) return false;
   }
-  if (f)
-    for (int r = 0; r < 16 * kMaxSteps; r++) {
-      f->row[r].g0 = geom[f->row[r].l0];
-      f->row[r].g1 = geom[f->row[r].l1];
-    }
+  for (int l = kLightQuadLevel0; withSide && l < a.moments.count; l++) {
+    LevelGeom &g = geom[l];
+    g.lightOfs = int(ofs);
+    g.mode |= 2;
+    ofs += 3LL * (a.moments.lv[l].w + 1) * (a.moments.lv[l].h + 1);
+  }
+  if (ofs > 0x7fffffffLL) return false;
+  if (sideFloat4s) *sideFloat4s = ofs;
   return true;
 }
 
 } // namespace
 
 uint64_t gatherScratchBytes(uint32_t width, uint32_t height, uint32_t mips) {
-  uint64_t quads = 0;
+  uint64_t entries = 0;
   for (uint32_t l = 0; l < mips && l < (uint32_t)kMaxGatherLevels; l++) {
     const uint64_t w = (width >> l) ? (width >> l) : 1, h = (height >> l) ? (height >> l) : 1;
-    quads += (w + 1) * (h + 1);
+    if (l >= (uint32_t)kDepthQuadLevel0) entries += (w + 1) * (h + 1);
+    if (l >= (uint32_t)kLightQuadLevel0) entries += 3 * (w + 1) * (h + 1);
   }
-  return quads * sizeof(float4);
+  return (entries ? entries : 1) * sizeof(float4);
 }
 
 cudaError_t launchGatherPack(const GatherArgs &a, void *scratch, cudaStream_t s) {
+  LevelGeom geom[kMaxGatherLevels];
+  if (!buildLevelGeometry(a, true, geom, nullptr)) return cudaErrorInvalidValue;
   PackArgs p;
-  if (!buildLevelGeometry(a, nullptr, &p)) return cudaErrorInvalidValue;
   p.moments = a.moments;
-  p.levels = a.moments.count;
+  p.light = a.light;
+  p.jobs = 0;
   int blocks = 0;
-  for (int l = 0; l < p.levels; l++) {
-    // strip: the march reaches ~13 level-l texels beyond the strip; the coarse levels are rebuilt whole
-    const int reach = 15; // quad row q reads moment rows q-1 and q: rows [strip-16, strip+16) of each level must be present (sharding.GATHER_REACH)
-    int r0 = (a.rows.y0 >> l) - reach, r1 = ((a.rows.y1 + (1 << l) - 1) >> l) + reach + 1;
-    const bool whole = l >= 6 || l == p.levels - 1; // the top level serves every clamped LOD
-    if (whole || r0 < 0) r0 = 0;
-    if (whole || r1 > p.quadRows[l]) r1 = p.quadRows[l];
-    p.rowBegin[l] = r0;
-    p.rowEnd[l] = r1;
-    p.blockBegin[l] = blocks;
-    blocks += ((p.quadPitch[l] + 31) / 32) * ((r1 - r0 + 7) / 8);
-  }
-  p.blockBegin[p.levels] = blocks;
+  for (int light = 0; light < 2; light++)
+    for (int l = light ? kLightQuadLevel0 : kDepthQuadLevel0; l < a.moments.count; l++) {
+      // strip: the march reaches ~13 level-l texels beyond the strip; the coarse levels are rebuilt whole
+      const int reach = 15; // entry row q reads rows q-1 and q: rows [strip-16, strip+16) of each level must be present (sharding.GATHER_REACH)
+      const int entryRows = a.moments.lv[l].h + 1;
+      int r0 = (a.rows.y0 >> l) - reach, r1 = ((a.rows.y1 + (1 << l) - 1) >> l) + reach + 1;
+      const bool whole = l >= 6 || l == a.moments.count - 1; // the top level serves every clamped LOD
+      if (whole || r0 < 0) r0 = 0;
+      if (whole || r1 > entryRows) r1 = entryRows;
+      const int j = p.jobs++;
+      p.jobLevel[j] = l;
+      p.jobLight[j] = light;
+      p.jobOfs[j] = light ? geom[l].lightOfs : geom[l].quadOfs;
+      p.jobPitch[j] = geom[l].quadPitch;
+      p.jobRowBegin[j] = r0;
+      p.jobRowEnd[j] = r1;
+      p.jobBlockBegin[j] = blocks;
+      blocks += ((geom[l].quadPitch + 31) / 32) * ((r1 - r0 + 7) / 8);
+    }
+  p.jobBlockBegin[p.jobs] = blocks;
   if (blocks == 0) return cudaSuccess;
-  packDepthQuadsKernel<<<blocks, 256, 0, s>>>(p, static_cast<float4 *>(scratch));
+  packSidePyramidKernel<<<blocks, 256, 0, s>>>(p, static_cast<float4 *>(scratch));
   return cudaGetLastError();
 }
 
 cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const void *scratch, cudaStream_t s) {
   if (a.rows.y1 <= a.rows.y0) return cudaSuccess;
   FastTables f;
-  if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, &f, nullptr)) return launchGatherStrict(a, t, s);
+  LevelGeom geom[kMaxGatherLevels];
+  if (!buildFastTables(a, t, &f) || !buildLevelGeometry(a, scratch != nullptr, geom, nullptr)) return launchGatherStrict(a, t, s);
+  for (int r = 0; r < 16 * kMaxSteps; r++) {
+    f.row[r].g0 = geom[f.row[r].l0];
+    f.row[r].g1 = geom[f.row[r].l1];
+  }
   const int rowsSpan = a.rows.y1 - (a.rows.y0 & ~3);
   const dim3 tiles((a.indirect.w + kTile - 1) / kTile, (rowsSpan + kTile - 1) / kTile);
-  static const int smCount = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  const float4 *quadsPtr = static_cast<const float4 *>(scratch);
-  if (!scratch) { // plain pyramids (lgcu_gi_gather without a scratch buffer): 64x64 tiles, all 16 pattern classes per CTA
-    gatherFastKernel<false, 4, kThreads><<<tiles, kThreads, 0, s>>>(a, f, nullptr, 0);
-    return cudaGetLastError();
-  }
+  int dev = 0, smCount = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev);
+  const float4 *side = static_cast<const float4 *>(scratch);
   // Work-unit granularity (measured, profiles/README.md): the 16 pattern classes of a tile are split over kSlices CTAs that are
   // neighbours in blockIdx.x, so they run at the same time and share the tile's pyramid neighbourhood through L2 (-5 % on a 4K frame,
   // -14 % on an 8K strip, DRAM traffic stays at the algorithmic bytes; 16 slices lose the L1 reuse between the passes of a tile);
   // grids of fewer than ~6 waves of 64x64 tiles (row strips, small frames) use 64x32 tiles so that the last wave's tail is shorter.
   constexpr int kSlices = 4;
   const bool smallTiles = (long long)tiles.x * tiles.y < 6LL * 4 * smCount;
-  if (smallTiles)
-    gatherFastKernel<true, 8, 128><<<dim3(tiles.x * kSlices, (rowsSpan + 31) / 32), 128, 0, s>>>(a, f, quadsPtr, kSlices);
+  const dim3 gridBig(tiles.x * kSlices, tiles.y), gridSmall(tiles.x * kSlices, (rowsSpan + 31) / 32);
+  // LGCU_GATHER_MINB: resident CTAs per SM the kernel is compiled for (A/B switch; 4 x 256 or 8 x 128 threads = 64 registers by default)
+  static const int minb = getenv("LGCU_GATHER_MINB") ? atoi(getenv("LGCU_GATHER_MINB")) : 4;
+  static const bool compact = getenv("LGCU_GATHER_WARP") ? atoi(getenv("LGCU_GATHER_WARP")) != 0 : false;
+#define LGCU_LAUNCH_GATHER(SIDE, MINB_BIG, MINB_SMALL, COMPACT)                                              \
+  do {                                                                                                        \
+    if (smallTiles)                                                                                           \
+      gatherFastKernel<SIDE, MINB_SMALL, 128, COMPACT><<<gridSmall, 128, 0, s>>>(a, f, side, kSlices);        \
+    else                                                                                                      \
+      gatherFastKernel<SIDE, MINB_BIG, kThreads, COMPACT><<<gridBig, kThreads, 0, s>>>(a, f, side, kSlices);  \
+  } while (0)
+  if (!side)
+    LGCU_LAUNCH_GATHER(false, 4, 8, false);
+  else if (minb == 5)
+    LGCU_LAUNCH_GATHER(true, 5, 10, false);
+  else if (compact)
+    LGCU_LAUNCH_GATHER(true, 4, 8, true);
   else
-    gatherFastKernel<true, 4, kThreads><<<dim3(tiles.x * kSlices, tiles.y), kThreads, 0, s>>>(a, f, quadsPtr, kSlices);
+    LGCU_LAUNCH_GATHER(true, 4, 8, false);
+#undef LGCU_LAUNCH_GATHER
   return cudaGetLastError();
 }
 

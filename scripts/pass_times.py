@@ -54,4 +54,4 @@ else:
         ev1.record(stream)
     r.sync()
     acc["GatherStage(rows %d..%d)" % ROWS] = ev0.elapsed_time(ev1) / n
-print(json.dumps({"fast_srgb": os.environ.get("LGCU_FAST_SRGB", "default"), "front_blocks": os.environ.get("LGCU_FRONT_BLOCKS", "default"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
+print(json.dumps({"gather_lock": os.environ.get("LGCU_GATHER_LOCK", "default"), "fast_srgb": os.environ.get("LGCU_FAST_SRGB", "default"), "front_blocks": os.environ.get("LGCU_FRONT_BLOCKS", "default"), "size": [W, H], "pass_ms": {k: round(v, 4) for k, v in acc.items()}}))
