@@ -40,6 +40,10 @@
 
 #include "lgcu_kernels.h"
 
+#ifndef LGCU_DEPTH_QUAD_LEVEL0
+#define LGCU_DEPTH_QUAD_LEVEL0 0
+#endif
+
 namespace lgcu {
 
 namespace {
@@ -47,7 +51,7 @@ namespace {
 constexpr int kTile = 64;      // pixels per tile edge
 constexpr int kThreads = 256;  // 16x16 pixels of one pattern class per pass
 constexpr int kMaxSteps = 12;  // march steps the tables hold (8 are reached for landscape viewports at any resolution)
-constexpr int kDepthQuadLevel0 = 0, kLightQuadLevel0 = 2; // first levels of the side pyramid's depth / light quads
+constexpr int kDepthQuadLevel0 = LGCU_DEPTH_QUAD_LEVEL0, kLightQuadLevel0 = 2; // first levels of the side pyramid's depth / light quads
 constexpr uint32_t F16 = LGCU_FORMAT_R16G16B16A16_SFLOAT, D32 = LGCU_FORMAT_D32_SFLOAT;
 constexpr float kFloorMagic = 12582912.0f; // 1.5 * 2^23: x + magic (rounded down) has floor(x) in its low mantissa bits
 constexpr int kFloorMagicBits = 0x4B400000;
@@ -141,7 +145,7 @@ struct Pyramids {
 // q = {quadOfs, quadPitch, lightOfs, mode}, tex = {texOfs, texPitch, wm1, hm1} of the level (the latter only read without quads)
 template <bool kSide> __device__ __forceinline__ float fetchDepth(const int4 q, const uint4 *texRow, const Footprint &f, const Pyramids &p) {
   float t00, t10, t01, t11;
-  if (kSide) {
+  if (kSide && (kDepthQuadLevel0 == 0 || (q.w & 1))) { // the same for every thread of the CTA
     const float4 v = __ldg(p.side + (unsigned)(q.x + (f.iy + 1) * q.y + (f.ix + 1)));
     t00 = v.x, t10 = v.y, t01 = v.z, t11 = v.w;
   } else {
