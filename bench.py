@@ -40,11 +40,18 @@ BYTES_PER_PX = {"resolve": 68.0, "light": 36.0, "mips": 26.67, "blur": 42.67, "g
 FRAME_BYTES_PER_PX = 258.67
 SHADOW_MAP_BYTES = 4 * 1024 * 1024
 METRIC = "full_gi_frame_mpix_per_s"
-# warp-level instructions one launch of the GI gather executes on the 4K synthetic frame, and the DRAM bytes it moves (ncu
-# smsp__inst_executed.sum, dram__bytes_read.sum + dram__bytes_write.sum of this scene's frame: profiles/r01l_gather_traffic_xslices.csv)
-GATHER_WARP_INST_4K = 1.314e9
-GATHER_DRAM_TRAFFIC_4K = 347067904 + 59241984
 SM_COUNT, ISSUE_PER_SM_PER_CLK = 148, 4  # 4 warp schedulers per SM, one warp instruction per scheduler per clock
+FP32_ISSUE_PER_SM_PER_CLK = 2.76           # measured scalar FFMA issue rate, warp instructions / clock / SM (profiles/r01e_fp32_pipe_rates.txt)
+
+
+def gather_ncu():
+    """ncu counters of the gather kernels of the CURRENT tree on the 4K bench frame (profiles/gather_ncu.json, written by
+    scripts/ncu_summary.py gather-json from the committed ncu CSV logs): DRAM bytes and executed instructions of the throughput kernel,
+    and the FP32 thread-instruction count of the shader-order kernel = the pass's algorithmic FP32 work."""
+    try:
+        return json.loads((ROOT / "profiles" / "gather_ncu.json").read_text())
+    except Exception:
+        return None
 
 
 def parse_args():
@@ -240,6 +247,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for name, ms in r.profile():
             pass_ms[name] = pass_ms.get(name, 0.0) + ms / prof_frames
     passes_per_frame = r.last_pass_count()
+    # the same frame with the reference's other denoiser setting (radius 2, SSVGIRenderer.h:288): per-pass times only
+    pass_ms_r2 = {}
+    r.render_frame(mode, 2, gi_flags)
+    r.sync()
+    for _ in range(prof_frames):
+        r.render_frame(mode, 2, gi_flags, profile=True)
+        r.sync()
+        for name, ms in r.profile():
+            pass_ms_r2[name] = pass_ms_r2.get(name, 0.0) + ms / prof_frames
+    r.render_frame(mode, 0, gi_flags)
+    r.sync()
 
     r.capture_frame(mode, 0, gi_flags)
     kernels_per_frame = r.captured_kernel_count()
@@ -380,21 +398,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         gather_ms = pass_ms.get("IndirectLightPass", 0.0)
         gather_bytes = BYTES_PER_PX["gather"] * npx
         frame_bytes = FRAME_BYTES_PER_PX * npx + SHADOW_MAP_BYTES
+        ncu = gather_ncu() if (W, H) == (3840, 2160) and not args.strict else None
         roofline = {
             "kernel": "gi_gather (IndirectLightPass)", "bound": "hbm", "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9 if gather_ms else None,
             "peak": peak, "unit": "GB/s", "frac": (gather_bytes / (gather_ms * 1e-3) / 1e9 / peak) if gather_ms else None,
-            "traffic": GATHER_DRAM_TRAFFIC_4K if (W, H) == (3840, 2160) and not args.strict else None, "algorithmic_bytes": gather_bytes,
-            "peak_source": peak_src, "ms": gather_ms,
-            "note": "the gather is FP32-ALU/L1 bound, not HBM bound (SURVEY.md F7): achieved = 41.33 B/px compulsory bytes / its measured time",
+            "traffic": ncu["fast"]["dram_bytes"] if ncu else None, "traffic_source": f"profiles/gather_ncu.json ({ncu['tag']})" if ncu else None,
+            "algorithmic_bytes": gather_bytes, "peak_source": peak_src, "ms": gather_ms,
+            "note": "the gather is bound by instruction issue and load latency, not by HBM (SURVEY.md F7): achieved = 41.33 B/px compulsory bytes / its measured time; "
+                    "see gather_fp32 for the roofline that bounds it",
         }
-        roofline_issue = None
-        if (W, H) == (3840, 2160) and gather_ms and not args.strict and clocks and clocks.get("sm_mhz"):
-            issue_peak = SM_COUNT * ISSUE_PER_SM_PER_CLK * clocks["sm_mhz"] * 1e6 / 1e9  # G warp-inst/s at the SM clock measured under load
-            issue_achieved = GATHER_WARP_INST_4K / (gather_ms * 1e-3) / 1e9
-            roofline_issue = {"kernel": "gi_gather (IndirectLightPass)", "bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "Gwarp-inst/s",
-                              "frac": issue_achieved / issue_peak, "warp_inst_per_launch": GATHER_WARP_INST_4K,
-                              "note": "the roofline that actually bounds the gather: warp instructions per launch (ncu, profiles/) / measured time, against "
-                                      "148 SMs x 4 schedulers x SM clock; its HBM figure above is reported because the contract asks for hbm|tensor"}
+        gather_fp32 = issue_util = None
+        if ncu and gather_ms and clocks and clocks.get("sm_mhz"):
+            clk = clocks["sm_mhz"] * 1e6
+            fp32_peak = SM_COUNT * FP32_ISSUE_PER_SM_PER_CLK * 32 * clk / 1e12  # T thread-instructions / s
+            alg = ncu["strict"]["fp32_thread_inst"]
+            gather_fp32 = {"kernel": "gi_gather (IndirectLightPass)", "bound": "fp32 issue", "algorithmic_fp32_thread_inst": alg,
+                           "achieved": alg / (gather_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "T thread-inst/s", "frac": alg / (gather_ms * 1e-3) / 1e12 / fp32_peak,
+                           "executed_fp32_thread_inst": ncu["fast"]["fp32_thread_inst"],
+                           "note": "algorithmic work = FP32 thread instructions the shader-order kernel executes on this frame (ncu smsp__sass_thread_inst_executed_op_fp32, "
+                                   "profiles/gather_ncu.json) / measured time, against 148 SMs x 2.76 warp-inst/clk (measured FFMA issue rate) x 32 lanes x the SM clock "
+                                   "under load; > 1 is possible because the throughput kernel needs fewer FP32 instructions than the shader's own order (affine rays, "
+                                   "no per-sample unprojection, atan only on hits)"}
+            issue_peak = SM_COUNT * ISSUE_PER_SM_PER_CLK * clk / 1e9
+            issue_util = {"kernel": "gi_gather (IndirectLightPass)", "executed_warp_inst": ncu["fast"]["warp_inst"], "rate": ncu["fast"]["warp_inst"] / (gather_ms * 1e-3) / 1e9,
+                          "issue_slots": issue_peak, "unit": "Gwarp-inst/s", "utilisation": ncu["fast"]["warp_inst"] / (gather_ms * 1e-3) / 1e9 / issue_peak,
+                          "note": "a UTILISATION figure, not a roofline fraction: instructions the kernel itself executes / issue slots available; it says how "
+                                  "much of the remaining time is stalls, not how good the kernel is"}
         roofline_frame = {"bound": "hbm", "achieved": frame_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak, "algorithmic_bytes": frame_bytes,
                           "note": "whole frame, pass-granular algorithmic bytes 258.67 B/px + 4 MiB shadow map"}
@@ -423,10 +452,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "gpu_launches": kernels_per_frame * args.steps,
             "kernels_per_frame": kernels_per_frame,
             "roofline": roofline,
-            "roofline_issue": roofline_issue,
+            "gather_fp32": gather_fp32,
+            "gather_issue_slot_utilisation": issue_util,
             "roofline_frame": roofline_frame,
             "frame_ms": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in frame_ms.items()},
             "pass_ms": {k: round(v, 4) for k, v in pass_ms.items()},
+            "pass_ms_denoiser_radius2": dict({k: round(v, 4) for k, v in pass_ms_r2.items()},
+                                             note="K6 with the 4x4 depth-guided fit (fused with K7): 24 B/px algorithmic = %.1f us at the measured HBM peak" % (24.0 * npx / (measured_peak_gbs()[0] * 1e9) * 1e6)),
             "pass_ms_mesh": {k: round(v, 4) for k, v in pass_ms_mesh.items()},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -58,7 +58,8 @@ def _stale(target: Path, sources) -> bool:
 def build_cuda(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     OBJ.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "lgcu.h"]
+    # this file is a dependency too: a changed flag in CUDA_UNITS must rebuild the unit
+    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "lgcu.h", Path(__file__)]
     objs = []
     with open(LIB / "nvcc_ptxas.log", "a") as log:  # ptxas -v output (registers, spills) of the units compiled by this call; git-ignored
         for unit, extra in CUDA_UNITS.items():

@@ -797,11 +797,11 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
                               void *stream) {
   int st = LGCU_OK;
   if (!dparams) return fail(LGCU_ERR_INVALID_ARGUMENT, "denoise_final_gather: null params");
-  if (dparams->radius != 0) { // only the default (copy) denoiser fuses; radius 2 runs as two passes
-    st = lgcu_denoise(dparams, noisy, normal, depthMoments, denoised, rows, stream);
-    if (st != LGCU_OK) return st;
-    return lgcu_final_gather(fparams, directLight, blurredDirectLight, albedo, denoised, swapchain, rows, stream);
-  }
+  (void)fparams;            // view/proj are uploaded by the reference (SSVGIRenderer.h:321-324) but unused by the shader
+  (void)blurredDirectLight; // sampled with weight 0 (finalGatherer.frag:52-57)
+  (void)normal;             // sampled by the denoiser but unused in its result (denoiser.frag:50, :77)
+  if (dparams->radius != 0 && dparams->radius != 2)
+    return fail(LGCU_ERR_UNSUPPORTED, "denoise_final_gather: radius %d (the shader hard-codes a 4x4 window for any non-zero radius; the reference passes 0 or 2)", dparams->radius);
   if (!indirectFormat(noisy) || !denoised || noisy->format != denoised->format)
     return fail(LGCU_ERR_UNSUPPORTED_FORMAT, "denoise_final_gather: noisy/denoised formats");
   if (!expectFormat(directLight, LGCU_FORMAT_R16G16B16A16_SFLOAT, "directLight", &st) || !expectFormat(albedo, LGCU_FORMAT_R16G16B16A16_SFLOAT, "albedo", &st) ||
@@ -809,6 +809,7 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
     return st;
   DenoiseFinalArgs a;
   a.indirectFormat = noisy->format;
+  a.radius = dparams->radius;
   a.viewport[0] = dparams->viewportExtent[0];
   a.viewport[1] = dparams->viewportExtent[1];
   if (!resolveLevel(noisy, 0, "noisy", &a.noisy, &st) || !resolveLevel(denoised, 0, "denoised", &a.denoised, &st) ||
@@ -818,6 +819,12 @@ int lgcu_denoise_final_gather(const lgcu_denoiser_data *dparams, const lgcu_fina
   if (!sameSize(a.swapchain, a.noisy, "swapchain", "noisy", &st) || !sameSize(a.swapchain, a.denoised, "swapchain", "denoised", &st) ||
       !sameSize(a.swapchain, a.directLight, "swapchain", "directLight", &st) || !sameSize(a.swapchain, a.albedo, "swapchain", "albedo", &st))
     return st;
+  if (a.radius != 0) {
+    if (!expectFormat(depthMoments, LGCU_FORMAT_R32G32_SFLOAT, "depthMoments", &st) || !resolveLevel(depthMoments, 0, "depthMoments", &a.depthMoments, &st)) return st;
+    if (!sameSize(a.noisy, a.depthMoments, "noisy", "depthMoments", &st)) return st;
+  } else {
+    a.depthMoments = a.noisy;
+  }
   a.rows = rowRange(rows, 0, a.swapchain.h);
   return cudaStatus(launchDenoiseFinalGather(a, static_cast<cudaStream_t>(stream)), "denoise_final_gather");
 }

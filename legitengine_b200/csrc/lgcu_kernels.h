@@ -93,8 +93,10 @@ struct FinalGatherArgs {
   RowRange rows;
 };
 
-struct DenoiseFinalArgs { // fused K6 (radius 0) + K7
+struct DenoiseFinalArgs { // fused K6 + K7
   uint32_t indirectFormat;
+  int radius;        // 0: centre tap (copy), 2: 4x4 depth-guided fit
+  LevelView depthMoments; // radius 2 only
   float viewport[2]; // DenoiserData.viewportExtent (the centre tap divides gl_FragCoord by it, denoiser.frag:83)
   LevelView noisy, denoised, directLight, albedo, swapchain;
   RowRange rows;

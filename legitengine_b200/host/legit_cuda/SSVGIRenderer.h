@@ -403,6 +403,11 @@ public:
     }
 
     const int denoiserRadius = options.denoiserRadius;
+    // The radius-2 denoiser reads indirectLight and depthMoments on rows -2..+1 around its own. A row strip of a frame that is sharded
+    // over GPUs does not own those rows of indirectLight and no stage exchanges them (sharding.py plans halos for radius 0), so the
+    // combination is refused instead of fitting stale rows at the seams.
+    if (useRows && denoiserRadius != 0 && (stages & FrameOptions::StageFinal) && (options.rows.y0 > 0 || options.rows.y1 < viewportExtent.height))
+      throw std::runtime_error("SSVGIRenderer: denoiserRadius != 0 on a row strip needs indirectLight halo rows that are not exchanged; render the frame whole");
     auto fillDenoiserData = [this, denoiserRadius](const PassData &pd) {
       pd.memoryPool->BeginSet();
       auto shaderDataBuffer = pd.memoryPool->GetUniformBufferData<lgcu_denoiser_data>("DenoiserData");

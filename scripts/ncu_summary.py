@@ -3,6 +3,7 @@
 
     python scripts/ncu_summary.py launches gpurun_out/launches_TAG.csv profiles/launches_TAG.md [kernels_per_frame]
     python scripts/ncu_summary.py full     gpurun_out/frame_TAG.ncu-rep profiles/frame_TAG.md
+    python scripts/ncu_summary.py gather-json profiles/STRICT.csv profiles/FAST.csv profiles/gather_ncu.json TAG
 """
 import csv
 import io
@@ -78,8 +79,41 @@ def full(src, dst):
     open(dst, "w").write("\n".join(out) + "\n")
 
 
+
+
+def gather_json(strict_csv, fast_csv, dst, tag):
+    """ncu --metrics CSV logs of the shader-order gather (algorithmic FP32 basis) and of the throughput gather + side-pyramid pack of the
+    same tree -> the small JSON bench.py reads for `roofline.traffic` and the FP32 figures (profiles/gather_ncu.json)."""
+    import json
+
+    def load(path):
+        rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+        hdr = rows[0]
+        k, m, v = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+        out = {}
+        for r in rows[1:]:
+            out.setdefault(short(r[k]), {})[r[m]] = float(r[v].replace(",", ""))
+        return out
+
+    def pick(d):
+        return {"warp_inst": d["smsp__inst_executed.sum"], "thread_inst": d["smsp__thread_inst_executed.sum"],
+                "fp32_thread_inst": d["smsp__sass_thread_inst_executed_op_fp32_pred_on.sum"], "fadd": d["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"],
+                "fmul": d["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"], "ffma": d["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum"],
+                "dram_bytes": d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"], "time_us_under_ncu": d["gpu__time_duration.sum"] / 1e3}
+
+    strict, fast = load(strict_csv), load(fast_csv)
+    out = {"tag": tag, "workload": "3840x2160 synthetic frame (seed 0xC0FFEE), one launch each, ncu --metrics ... --clock-control none",
+           "sources": [strict_csv, fast_csv]}
+    for name, d in list(strict.items()) + list(fast.items()):
+        key = "strict" if "Strict" in name else ("pack" if "pack" in name else "fast")
+        out[key] = dict(pick(d), kernel=name)
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
+    elif sys.argv[1] == "gather-json":
+        gather_json(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
     else:
         full(sys.argv[2], sys.argv[3])
