@@ -52,6 +52,11 @@ int lgh_use_mesh(lgh_renderer *r, uint32_t enable);
 /* DebugRenderer::RenderImageViews over the finished frame (SSVGIRenderer.h:344-350): off by default — the reference always draws
  * it, the parity tests and the bench look at the frame before it. Takes effect with the next lgh_render_frame / lgh_capture_frame. */
 int lgh_set_debug_overlay(lgh_renderer *r, uint32_t enable);
+/* Puts another B8G8R8A8_SRGB image of the viewport's size and the canonical layout behind the swapchain proxy — the reference's
+ * swapchain view is an external image-view proxy too (LV/PresentQueue.h:106-110). deviceBase may be memory of a PEER GPU (CUDA IPC
+ * mapping): a strip-sharded frame then composites by writing every strip straight into the presenting GPU's image. NULL restores the
+ * renderer's own image. Not allowed while a captured frame exists (re-capture afterwards). */
+int lgh_set_external_swapchain(lgh_renderer *r, void *deviceBase);
 
 /* One frame: SSVGIRenderer::RenderFrame + RenderGraph::Execute. rows may be NULL (whole frame; required for pass-granular).
  * profile != 0 records per-pass GPU events (read them with lgh_get_profile after lgh_sync). */

@@ -603,11 +603,12 @@ int lgcu_raster_gbuffer(const lgcu_gbuffer_builder_data *params, const lgcu_mesh
 int lgcu_copy_rows(const lgcu_row_copy *copies, uint32_t count, void *stream) {
   if (!copies && count) return fail(LGCU_ERR_INVALID_ARGUMENT, "copy_rows: null list");
   const int sms = smCountOfCurrentDevice();
-  for (uint32_t begin = 0; begin < count; begin += kMaxCopies) {
+  for (uint32_t next = 0; next < count;) { // chunks of kMaxCopies non-empty slabs; `next` = first entry not consumed yet
     RowCopyArgs a;
     a.count = 0;
     uint64_t units = 0;
-    for (uint32_t i = begin; i < count && a.count < kMaxCopies; i++) {
+    for (; next < count && a.count < kMaxCopies; next++) {
+      const uint32_t i = next;
       const lgcu_row_copy &c = copies[i];
       if (!c.bytes) continue;
       if (!c.src || !c.dst || (c.bytes % 16) != 0 || (reinterpret_cast<uintptr_t>(c.src) % 16) != 0 || (reinterpret_cast<uintptr_t>(c.dst) % 16) != 0)
@@ -618,6 +619,7 @@ int lgcu_copy_rows(const lgcu_row_copy *copies, uint32_t count, void *stream) {
       a.unitEnd[a.count] = units;
       a.count++;
     }
+    if (a.count == 0) continue;
     const int st = cudaStatus(launchRowCopies(a, sms, static_cast<cudaStream_t>(stream)), "copy_rows");
     if (st != LGCU_OK) return st;
   }

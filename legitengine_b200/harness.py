@@ -43,6 +43,7 @@ def load_harness() -> C.CDLL:
         lib.lgh_upload_mesh.argtypes = [R, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         lib.lgh_use_mesh.argtypes = [R, C.c_uint32]
         lib.lgh_set_debug_overlay.argtypes = [R, C.c_uint32]
+        lib.lgh_set_external_swapchain.argtypes = [R, C.c_void_p]
         lib.lgh_render_frame.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         lib.lgh_render_stages.argtypes = [R, C.c_uint32, C.c_int32, C.c_uint32, abi.ROWS, C.c_uint32]
         H64 = C.c_ubyte * 64
@@ -123,6 +124,11 @@ class Renderer:
     def set_debug_overlay(self, enable: bool) -> None:
         """DebugInfoPass (thumbnails of normal / albedo / indirectLight / denoisedIndirectLight) over the finished frame."""
         _check(self.lib.lgh_set_debug_overlay(self.handle, 1 if enable else 0), "lgh_set_debug_overlay")
+
+    def set_external_swapchain(self, device_base: int) -> None:
+        """The frame's swapchain target becomes the image at `device_base` (canonical layout of a W x H BGRA8 image; may be a peer GPU's
+        memory through a CUDA-IPC mapping). 0 restores the renderer's own image."""
+        _check(self.lib.lgh_set_external_swapchain(self.handle, C.c_void_p(device_base or None)), "lgh_set_external_swapchain")
 
     def use_mesh(self, enable: bool) -> None:
         _check(self.lib.lgh_use_mesh(self.handle, 1 if enable else 0), "lgh_use_mesh")

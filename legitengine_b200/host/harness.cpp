@@ -267,6 +267,25 @@ int lgh_set_debug_overlay(lgh_renderer *r, uint32_t enable) {
   return LGCU_OK;
 }
 
+int lgh_set_external_swapchain(lgh_renderer *r, void *deviceBase) {
+  if (!r) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_set_external_swapchain: null renderer");
+  LGH_TRY({
+    // the swapchain view is an EXTERNAL image-view proxy, as in the reference (LV/PresentQueue.h:106-110): swap the image behind it
+    lgcu_image desc = r->swapchainImage->GetDesc();
+    r->swapchainProxy.Reset();
+    r->swapchainView.reset();
+    if (deviceBase) {
+      desc.base = deviceBase;
+      r->swapchainImage.reset(new ImageData(desc)); // non-owning: e.g. the presenting GPU's swapchain image through a peer mapping
+    } else {
+      r->swapchainImage.reset(new ImageData(vk::Format::eB8G8R8A8Srgb, glm::uvec2(r->width, r->height), 1));
+    }
+    r->swapchainView.reset(new ImageView(r->swapchainImage.get(), 0, 1));
+    r->swapchainProxy = r->core->GetRenderGraph()->AddExternalImageView(r->swapchainView.get(), ImageUsageTypes::Present);
+    return LGCU_OK;
+  })
+}
+
 int lgh_run_interleave(lgh_renderer *r, const char *srcName, uint32_t gridX, uint32_t gridY, void *hostDeinterleaved, void *hostRoundTrip, uint64_t hostPitchBytes) {
   if (!r || !srcName || !hostDeinterleaved || !hostRoundTrip) return setError(LGCU_ERR_INVALID_ARGUMENT, "lgh_run_interleave: null argument");
   ImageView *src = r->findImage(srcName);

@@ -142,16 +142,21 @@ class P2PStripRenderer(StripRenderer):
         chains | signal CHAINS=F to gather pullers | wait CHAINS >= F from gather sources | pull gather halos | signal ACK=F to my sources
         gather + final | pushers: wait FREE >= F, push strip into root's swapchain, signal DELIVERED=F | root: wait DELIVERED >= F
 
+    With `direct_present` (default) there is no push: a non-root rank's swapchain target IS the root's image (peer mapping put behind the
+    renderer's external swapchain proxy), so the composite kernel's BGRA8 stores travel over NVLink while it runs; the rank waits
+    FREE >= F before gather + final and signals DELIVERED=F after it.
     No wait depends on a later signal of the waiting GPU, streams are in order, so the protocol cannot deadlock."""
 
     FRONT, CHAINS, DELIVERED, ACK, FREE = range(5)
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, *args, direct_present: bool = True, **kwargs):
+        stream = kwargs.get("stream")
+        if not stream:
+            raise ValueError("P2PStripRenderer needs an explicit CUDA stream, passed as stream=... (the same one the harness renders on)")
         super().__init__(*args, **kwargs)
         self._lgcu = abi.load_lgcu()
-        if not kwargs.get("stream"):
-            raise ValueError("P2PStripRenderer needs an explicit CUDA stream (the same one the harness renders on)")
-        self._stream = C.c_void_p(kwargs["stream"])
+        self._stream = C.c_void_p(stream)
+        self._direct_present = direct_present
         self._ready = False
         self._peer_ptrs: List[int] = []
 
@@ -203,6 +208,10 @@ class P2PStripRenderer(StripRenderer):
         pp = self.plan_present if self.present else []
         self._counter = C.c_void_p(self._flags + 4 * (5 * world))
         self._pull_chains, self._pull_gather, self._push = copies(pc, True), copies(pg, True), copies(pp, False)
+        if self._direct_present and self.present and rank != self.root and self.rows[1] > self.rows[0]:
+            # composite without a copy: this rank's final pass writes its strip straight into the presenting GPU's swapchain image
+            self.renderer.set_external_swapchain(base[self.root]["swapchain"])
+            self._push = ((abi.RowCopy * 1)(), 0)
         chain_pullers, chain_sources = {t.dst for t in pc if t.src == rank}, {t.src for t in pc if t.dst == rank}
         gather_pullers, gather_sources = {t.dst for t in pg if t.src == rank}, {t.src for t in pg if t.dst == rank}
         pushers = {t.src for t in pp}
@@ -267,12 +276,16 @@ class P2PStripRenderer(StripRenderer):
         self._copy(self._pull_gather)
         self._signal(self._sig_ack)
         mark()
+        direct = self._direct_present and self._is_pusher
+        if direct:
+            self._wait(self._wait_free)  # the presenting GPU is done with the previous frame's image
         if have:
             r.render_stages(harness.STAGE_GATHER | harness.STAGE_FINAL, rows, gi_flags=gi_flags)
         mark()
         if self._is_pusher:
-            self._wait(self._wait_free)
-            self._copy(self._push)
+            if not direct:
+                self._wait(self._wait_free)
+                self._copy(self._push)
             self._signal(self._sig_delivered)
         self._wait(self._wait_delivered)
         mark()

@@ -180,3 +180,18 @@ def run_pass_list(be, fi: FrameImages, p: FrameParams, inputs: Dict[str, object]
     be.denoise(C.byref(p.denoiser), v(fi.indirectLight), v(fi.normal), v(fi.depthMoments), v(fi.denoisedIndirectLight), r)
     be.final_gather(C.byref(p.final), v(fi.directLight), v(fi.blurredDirectLight), v(fi.albedo), v(fi.denoisedIndirectLight),
                     v(fi.swapchain), r)
+
+
+def debug_tiles(count: int):
+    """QuadData of the first `count` tiles, in the fp32 arithmetic of DebugRenderer.h:27-57."""
+    f = np.float32
+    size, pad = f(0.1), f(0.02)
+    x, y = pad, pad
+    out = []
+    for _ in range(count):
+        out.append(abi.DebugQuadData((C.c_float * 4)(float(x), float(y), float(f(x + size)), float(f(y + size)))))
+        x = f(x + f(size + pad))
+        if f(x + size) > f(1.0):
+            x = pad
+            y = f(y + f(size + pad))
+    return out

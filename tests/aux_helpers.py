@@ -52,19 +52,7 @@ def equal_nan_aware(a: images.HostImage, b: images.HostImage, level: int) -> boo
     return bool(np.all(same | both_nan_only))
 
 
-def debug_tiles(count: int):
-    """QuadData of the first `count` tiles, in the fp32 arithmetic of DebugRenderer.h:27-57."""
-    f = np.float32
-    size, pad = f(0.1), f(0.02)
-    x, y = pad, pad
-    out = []
-    for _ in range(count):
-        out.append(abi.DebugQuadData((C.c_float * 4)(float(x), float(y), float(f(x + size)), float(f(y + size)))))
-        x = f(x + f(size + pad))
-        if f(x + size) > f(1.0):
-            x = pad
-            y = f(y + f(size + pad))
-    return out
+from legitengine_b200.passes import debug_tiles  # noqa: E402,F401  (host-side tile layout of DebugRenderer.h:27-57)
 
 
 # ---- committed golden fixture of these passes (tests/golden/aux_passes.npz: outputs of the reference's own SPIR-V, make_golden.py) ----

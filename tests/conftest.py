@@ -40,5 +40,9 @@ def _built():
     if not (ROOT / "oracle" / "liboracle_port.so").exists():
         _build.build_oracle()
     if not (ROOT / "legitengine_b200" / "lib" / "liblgcu.so").exists():
-        _build.build_cuda()
+        import shutil
+
+        if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
+            _build.build_cuda()  # cross-compiles without a GPU; the ABI tests then load it
+        # without nvcc the CPU tests that need the library skip themselves (abi.LibraryMissing), the others run
     yield

@@ -34,7 +34,7 @@ def _neighbours(bounds, width, height, root=0):
     return info
 
 
-def _program(rank, info, root, frames, ack_wait=True):
+def _program(rank, info, root, frames, ack_wait=True, direct_present=False):
     """The operation list of one rank's stream for `frames` frames, in the order P2PStripRenderer.render() enqueues it.
     ops: ("bump",) | ("signal", stage, targets) | ("wait", stage, writers, lag) | ("work", name, reads, writes)
     resources are (owner rank, name); reads carry the frame the data must belong to."""
@@ -55,11 +55,16 @@ def _program(rank, info, root, frames, ack_wait=True):
         ops.append(("wait", CHAINS, me["gather_sources"], 0))
         ops.append(("work", "pull_gather", [(s, "blurred") for s in me["gather_sources"]] + [(s, "blurred0") for s in me["gather_sources"]], [(rank, "blurred_halo")]))
         ops.append(("signal", ACK, me["chain_sources"] | me["gather_sources"]))
-        ops.append(("work", "gather_final", [(rank, "blurred"), (rank, "blurred0"), (rank, "blurred_halo")], [(rank, "swap")]))
-        if me["pusher"]:
+        if direct_present and me["pusher"]:  # the final pass writes the strip straight into the root's swapchain image
             ops.append(("wait", FREE, {root}, 0))
-            ops.append(("work", "push", [(rank, "swap")], [(root, f"swap_from_{rank}")]))
+            ops.append(("work", "gather_final", [(rank, "blurred"), (rank, "blurred0"), (rank, "blurred_halo")], [(root, f"swap_from_{rank}")]))
             ops.append(("signal", DELIVERED, {root}))
+        else:
+            ops.append(("work", "gather_final", [(rank, "blurred"), (rank, "blurred0"), (rank, "blurred_halo")], [(rank, "swap")]))
+            if me["pusher"]:
+                ops.append(("wait", FREE, {root}, 0))
+                ops.append(("work", "push", [(rank, "swap")], [(root, f"swap_from_{rank}")]))
+                ops.append(("signal", DELIVERED, {root}))
         if rank == root:
             ops.append(("wait", DELIVERED, me["pushers"], 0))
             ops.append(("work", "present", [(root, "swap")] + [(root, f"swap_from_{p}") for p in me["pushers"]], []))
@@ -70,10 +75,10 @@ class Hazard(AssertionError):
     pass
 
 
-def _simulate(world, bounds, width, height, frames, seed, ack_wait=True, root=0):
+def _simulate(world, bounds, width, height, frames, seed, ack_wait=True, root=0, direct_present=False):
     rng = random.Random(seed)
     info = _neighbours(bounds, width, height, root)
-    programs = [_program(r, info, root, frames, ack_wait) for r in range(world)]
+    programs = [_program(r, info, root, frames, ack_wait, direct_present) for r in range(world)]
     pc = [0] * world            # next op of every rank
     in_flight = [None] * world  # the "work" op a rank has begun and not yet ended
     frame = [0] * world         # device-side frame counter of every rank
@@ -129,14 +134,17 @@ def _simulate(world, bounds, width, height, frames, seed, ack_wait=True, root=0)
     return steps
 
 
+@pytest.mark.parametrize("direct_present", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-def test_frame_protocol_has_no_deadlock_and_no_data_hazard(world):
+def test_frame_protocol_has_no_deadlock_and_no_data_hazard(world, direct_present):
+    """Both composites: the strip pushed by a copy after the final pass, and (default) the final pass writing it straight into the
+    presenting GPU's swapchain image."""
     width, height = 7680, 4320
     even = sharding.strip_bounds(height, world)
     uneven = sharding.rebalance_bounds(even, [1.0 + 0.3 * ((r * 5) % 4) for r in range(world)], height)
     for bounds in (even, uneven):
         for seed in range(60):
-            assert _simulate(world, bounds, width, height, frames=4, seed=seed) > 0
+            assert _simulate(world, bounds, width, height, frames=4, seed=seed, direct_present=direct_present) > 0
 
 
 def test_small_frame_where_strips_reach_beyond_their_neighbours():
