@@ -75,7 +75,7 @@ def parse_args():
     ap.add_argument("--strip-input", default="fragments", choices=["fragments", "mesh"],
                     help="strips: what every rank starts from — its strip of the pre-rasterised fragment buffer (uploaded per frame in the e2e leg), or the "
                          "mesh scene, which every rank rasterises for its own rows on the device (ShadowPass + GBufferRasterPass with lgcu_rows)")
-    ap.add_argument("--balance", type=int, default=3, help="strips (p2p): up to this many measure -> rebalance rounds of the strip boundaries (0 = equal rows)")
+    ap.add_argument("--balance", type=int, default=5, help="strips (p2p): up to this many measure -> rebalance rounds of the strip boundaries (0 = equal rows)")
     ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -532,12 +532,14 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     cls = multigpu.P2PStripRenderer if args.transport == "p2p" else multigpu.StripRenderer
     gi_flags = abi.GI_STRICT if args.strict else abi.GI_DEFAULT
 
-    mesh = scene.scene_mesh(seed) if args.strip_input == "mesh" else None
+    scene_mesh = scene.scene_mesh(seed)
+    mesh = scene_mesh if args.strip_input == "mesh" else None
 
-    def build(bounds):
-        """Strip renderer for `bounds` with this rank's strip of the rasterised scene generated into pinned memory and uploaded."""
+    def build(bounds, mesh=mesh):
+        """Strip renderer for `bounds` with this rank's strip of the rasterised scene generated into pinned memory and uploaded
+        (or, with `mesh`, the scene in the reference's form: every rank then rasterises its own rows in the front stage)."""
         y0, y1 = bounds[rank]
-        frag_host = torch.empty((max(y1 - y0, 1), W * 32), dtype=torch.uint8).pin_memory()
+        frag_host = torch.empty((max(y1 - y0, 1) if mesh is None else 1, W * 32), dtype=torch.uint8).pin_memory()
         frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
         if mesh is None:
             scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
@@ -545,7 +547,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         sr.renderer.upload_objects(objects.ctypes.data, len(objects))
         sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
         ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
-        if args.strip_input == "mesh":
+        if mesh is not None:
             sr.renderer.upload_mesh(mesh)  # the front stage then rasterises this rank's rows itself
         else:
             sr.upload_strip(ptr, W * 32)
@@ -614,21 +616,33 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         ms_per_step = ms_total / args.steps
         received = sr.received_bytes
 
+        recv_all = torch.tensor([received], device="cuda", dtype=torch.int64)
+        dist.all_reduce(recv_all)
+        # per-rank, per-stage GPU time of un-captured frames (events between the stages on every rank): shows where a strip waits
+        stage_ms = stage_profile(sr) if args.transport == "p2p" else None
+
+        # --- e2e: like the single-GPU line, the frame starts from the SCENE in host memory (vertex / index buffers, draw list, per-object
+        # constants uploaded by every rank every step, rasterised for the rank's own rows on the device) and ends with the composited
+        # swapchain image in the presenting rank's pinned host memory
+        if mesh is None:
+            torch.cuda.synchronize()
+            sr.release_graph()
+            dist.barrier()
+            sr.close()
+            del frag_host
+            sr, frag_host, full_view_ptr = build(bounds, scene_mesh)
+            if use_graph:
+                sr.capture(gi_flags)
+            frame = sr.replay if use_graph else (lambda: sr.render(gi_flags))
+
         def e2e_step():
-            if mesh is not None:
-                sr.renderer.upload_mesh(mesh)
-            else:
-                sr.upload_strip(full_view_ptr, W * 32)
+            sr.renderer.upload_mesh(scene_mesh)
             frame()
             if rank == 0:
                 sr.renderer.download_swapchain(swap_host.data_ptr(), W * 4)
 
         e2e_steps = args.e2e_steps or min(args.steps, 30)
         e2e_ms, _ = timed(e2e_step, e2e_steps, 3)
-        recv_all = torch.tensor([received], device="cuda", dtype=torch.int64)
-        dist.all_reduce(recv_all)
-        # per-rank, per-stage GPU time of un-captured frames (events between the stages on every rank): shows where a strip waits
-        stage_ms = stage_profile(sr) if args.transport == "p2p" else None
     # --- the same run's single-GPU frame of this workload (rank 0 alone; the others wait), and BASELINE configs[4]'s throughput mode:
     # every GPU renders independent 4K frames (same scene on every rank, so that the MAX over ranks measures the GPUs, not the scenes)
     extra_steps = max(10, min(args.steps, 50))
@@ -658,9 +672,11 @@ def run_strips(args, rank: int, world: int, local_rank: int):
             },
             "clocks": clocks,
             "e2e": {"value": npx / (e2e_ms / e2e_steps * 1e-3) / 1e6, "unit": "Mpix/s",
-                    "h2d_bytes_per_step": (W * H * 32) if mesh is None else world * sum(a.nbytes for a in (mesh.vertices, mesh.indices, mesh.draws, mesh.objects)),
+                    "h2d_bytes_per_step": world * sum(a.nbytes for a in (scene_mesh.vertices, scene_mesh.indices, scene_mesh.draws, scene_mesh.objects)),
                     "d2h_bytes_per_step": W * H * 4,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "input": "scene as the reference holds it, uploaded by every rank from host memory every step and rasterised for the rank's own rows on the "
+                             "device; output: the composited BGRA8 swapchain image from the presenting rank to pinned host memory (PCIe-bound at 8K: 133 MB per frame)"},
             "gpu_launches": 6 * args.steps * world,
             "kernels_per_frame": 6,
             "single_gpu": {"ms_per_step": single_ms, "value": npx / (single_ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": extra_steps,

@@ -553,11 +553,14 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   int dev = 0, smCount = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, dev);
   const float4 *side = static_cast<const float4 *>(scratch);
-  // Work-unit granularity (measured, profiles/README.md): the 16 pattern classes of a tile are split over kSlices CTAs that are
-  // neighbours in blockIdx.x, so they run at the same time and share the tile's pyramid neighbourhood through L2 (-5 % on a 4K frame,
-  // -14 % on an 8K strip, DRAM traffic stays at the algorithmic bytes; 16 slices lose the L1 reuse between the passes of a tile);
-  // grids of fewer than ~6 waves of 64x64 tiles (row strips, small frames) use 64x32 tiles so that the last wave's tail is shorter.
-  constexpr int kSlices = 4;
+  // Work-unit granularity (measured, profiles/README.md): the 16 pattern classes of a tile are split over `slices` CTAs that are
+  // neighbours in blockIdx.x, so they run at the same time and share the tile's pyramid neighbourhood through L2 (DRAM traffic stays at
+  // 1.2x the algorithmic bytes). Whole 4K / 8K frames are indifferent to 4, 8 or 16 slices (1.348 / 1.346 / 1.354 ms at 4K; 5.05 / 5.08 /
+  // 5.12 ms at 8K); grids of a few waves — a multi-GPU row strip, a 1080p frame — gain 4-5 % from 16 (one class per CTA: the shortest
+  // tail), r02q. Grids of fewer than ~6 waves of 64x64 tiles also use 64x32 tiles.
+  static const int envSlices = getenv("LGCU_GATHER_SLICES") ? atoi(getenv("LGCU_GATHER_SLICES")) : 0; // A/B switch: 1, 2, 4, 8 or 16
+  const long long tileCount = (long long)tiles.x * tiles.y;
+  const int kSlices = (envSlices == 1 || envSlices == 2 || envSlices == 4 || envSlices == 8 || envSlices == 16) ? envSlices : (tileCount < 10LL * smCount ? 16 : 4);
   const bool smallTiles = (long long)tiles.x * tiles.y < 6LL * 4 * smCount;
   const dim3 gridBig(tiles.x * kSlices, tiles.y), gridSmall(tiles.x * kSlices, (rowsSpan + 31) / 32);
   // LGCU_GATHER_MINB: resident CTAs per SM the kernel is compiled for (A/B switch; 4 x 256 or 8 x 128 threads = 64 registers by default)

@@ -50,7 +50,8 @@ struct lgh_renderer {
   bool useMesh = false;
   bool debugOverlay = false;
 
-  std::unique_ptr<ImageData> swapchainImage;
+  std::unique_ptr<ImageData> swapchainImage;         // the renderer's own image (kept while an external one is in use: peers may map it)
+  std::unique_ptr<ImageData> externalSwapchainImage; // non-owning wrapper of the image lgh_set_external_swapchain put behind the proxy
   std::unique_ptr<ImageView> swapchainView;
   RenderGraph::ImageViewProxyUnique swapchainProxy;
 
@@ -274,13 +275,12 @@ int lgh_set_external_swapchain(lgh_renderer *r, void *deviceBase) {
     lgcu_image desc = r->swapchainImage->GetDesc();
     r->swapchainProxy.Reset();
     r->swapchainView.reset();
+    r->externalSwapchainImage.reset();
     if (deviceBase) {
       desc.base = deviceBase;
-      r->swapchainImage.reset(new ImageData(desc)); // non-owning: e.g. the presenting GPU's swapchain image through a peer mapping
-    } else {
-      r->swapchainImage.reset(new ImageData(vk::Format::eB8G8R8A8Srgb, glm::uvec2(r->width, r->height), 1));
+      r->externalSwapchainImage.reset(new ImageData(desc)); // non-owning: e.g. the presenting GPU's swapchain image through a peer mapping
     }
-    r->swapchainView.reset(new ImageView(r->swapchainImage.get(), 0, 1));
+    r->swapchainView.reset(new ImageView(deviceBase ? r->externalSwapchainImage.get() : r->swapchainImage.get(), 0, 1));
     r->swapchainProxy = r->core->GetRenderGraph()->AddExternalImageView(r->swapchainView.get(), ImageUsageTypes::Present);
     return LGCU_OK;
   })

@@ -176,7 +176,14 @@ class P2PStripRenderer(StripRenderer):
             if peer == rank:
                 base.append({name: int(self.renderer.image_desc(name).base) for name in self.EXCHANGED} | {"__flags__": self._flags})
             else:
-                opened = {name: harness.ipc_open(h) for name, h in everyone[peer].items()}
+                opened = {}
+                for name, h in everyone[peer].items():
+                    if name == "swapchain" and peer != self.root:
+                        continue  # only the presenting rank's swapchain image is ever written by a peer
+                    try:
+                        opened[name] = harness.ipc_open(h)
+                    except RuntimeError as e:
+                        raise RuntimeError(f"rank {rank}: cannot map '{name}' of rank {peer} ({e}); mapped so far from that rank: {sorted(opened)}") from e
                 self._peer_ptrs += list(opened.values())
                 base.append(opened)
         desc = {name: self.renderer.image_desc(name) for name in self.EXCHANGED}
@@ -211,6 +218,7 @@ class P2PStripRenderer(StripRenderer):
         if self._direct_present and self.present and rank != self.root and self.rows[1] > self.rows[0]:
             # composite without a copy: this rank's final pass writes its strip straight into the presenting GPU's swapchain image
             self.renderer.set_external_swapchain(base[self.root]["swapchain"])
+            self._external_swapchain = True
             self._push = ((abi.RowCopy * 1)(), 0)
         chain_pullers, chain_sources = {t.dst for t in pc if t.src == rank}, {t.src for t in pc if t.dst == rank}
         gather_pullers, gather_sources = {t.dst for t in pg if t.src == rank}, {t.src for t in pg if t.dst == rank}
@@ -303,9 +311,14 @@ class P2PStripRenderer(StripRenderer):
     def close(self):
         self._torch.cuda.synchronize()
         self.dist.barrier()  # nobody may still be reading this rank's memory
+        if getattr(self, "_external_swapchain", False):
+            self.renderer.set_external_swapchain(0)  # drop the view of the presenting GPU's image before its mapping goes
         for p in self._peer_ptrs:
             harness.ipc_close(p)
         self._peer_ptrs = []
+        # every mapping of this rank's memory is closed before the memory is freed: a peer that still held the old mapping while this
+        # rank re-allocated and re-exported the same block could not open the new handle (cudaIpcOpenMemHandle: invalid argument)
+        self.dist.barrier()
         if self._ready:
             harness.device_free(self._flags)
         super().close()
