@@ -101,6 +101,9 @@ def build_oracle() -> None:
     _run(["make", "-C", ROOT / "oracle", "port"], env=env)
     if Path("/root/reference/dependencies/spirv-cross/spirv_cpp.cpp").exists():
         _run(["make", "-C", ROOT / "oracle", "-j8", "ref"], env=env)
+        packed = ROOT / "oracle" / "_ref" / "bundled_sponza_mesh.npz"
+        if not packed.exists():  # BASELINE configs[0]: the reference's bundled scene, packed for the GPU box (git-ignored like the .so above)
+            _run([sys.executable, ROOT / "oracle" / "make_bundled_mesh.py"], env=env)
 
 
 def build_all(force: bool = False) -> None:

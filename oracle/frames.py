@@ -18,8 +18,15 @@ def oracle_mesh_frame(seed: int, width: int, height: int, camera_key: Tuple = No
     from legitengine_b200 import raster
 
     camera = dict(pos=camera_key[0], vert=camera_key[1], hor=camera_key[2]) if camera_key else None
-    m = scene.frame_matrices(width, height, camera=camera)
     mesh = scene.scene_mesh(seed, n_boxes)
+    return (mesh, camera) + oracle_frame_from_mesh(mesh, width, height, camera, denoise_radius, seed)
+
+
+def oracle_frame_from_mesh(mesh, width: int, height: int, camera=None, denoise_radius: int = 0, seed: int = 0):
+    """(scene the mesh rasterises to under the oracle's rasteriser, params, the port oracle's frame images)."""
+    from legitengine_b200 import raster
+
+    m = scene.frame_matrices(width, height, camera=camera)
     port, ms = loader.port(), raster.host_mesh_desc(mesh)
     frags = np.zeros((height, width), dtype=abi.FRAGMENT_DTYPE)
     g = abi.GBufferBuilderData(abi.mat4(m.view), abi.mat4(m.proj), 0.0, 0.0)
@@ -31,4 +38,4 @@ def oracle_mesh_frame(seed: int, width: int, height: int, camera_key: Tuple = No
     p = passes.make_params(width, height, m, denoise_radius)
     fi = passes.FrameImages(width, height, images.HostImage)
     passes.run_pass_list(port, fi, p, passes.upload_inputs(fi, sc))
-    return mesh, camera, sc, p, fi
+    return sc, p, fi

@@ -34,3 +34,29 @@ def test_bundled_scene_frame_vs_reference_fixture(cu, mode):
     _sync()
     H.assert_images_radiance(dev2.indirectLight.to_host(), ref.indirectLight, f"bundled Sponza {mode}: gather on the fixture's pyramids",
                              exact=None if mode == "strict" else H.exact_gather(p, ref, (0, ref.height)))
+
+
+def test_bundled_scene_512_from_the_mesh():
+    """BASELINE configs[0] at its own size: the bundled scene (SponzaScene.json: 364 157 triangles in 5 draws, packed by
+    oracle/make_bundled_mesh.py where /root/reference exists) rendered 512x512 from its vertex / index buffers — ShadowPass and
+    GBufferRasterPass on the device (the large-scene path of k_raster.cu), then the fused frame — against the oracle's rasteriser
+    feeding the oracle's passes: shadow map and G-buffer bit-exact, every later stage at the one bar on its own inputs."""
+    from legitengine_b200 import abi, harness
+    from oracle import frames as OF
+    from oracle import make_bundled_mesh as MB
+
+    mesh = MB.load()
+    if mesh is None:
+        pytest.skip("oracle/_ref/bundled_sponza_mesh.npz not generated (needs /root/reference at build time)")
+    W = Hh = 512
+    sc, p, ref = OF.oracle_frame_from_mesh(mesh, W, Hh)
+    r = harness.Renderer(W, Hh)
+    r.upload_mesh(mesh)
+    r.render_frame(harness.MODE_FUSED, 0, abi.GI_DEFAULT, profile=True)
+    r.sync()
+    names = [n for n, _ in r.profile()]
+    assert names[0] == "ShadowPass" and names[1] == "GBufferRasterPass", names
+    for n in ("shadowMap", "albedo", "emissive", "normal", "depthStencil"):
+        H.assert_bit_exact(r.download_image(n), getattr(ref, n), 0, n)
+    H.stagewise_check(r.download_image, p, ref, what="bundled Sponza 512x512 from the mesh")
+    r.close()
