@@ -34,6 +34,7 @@ CUDA_UNITS = {
     "k_raster.cu": ["-fmad=false"],
     "k_aux.cu": ["-fmad=false"],
     "lgcu_api.cu": ["-fmad=false"],
+    "lgcu_interop.cu": [],
 }
 
 
@@ -59,7 +60,7 @@ def build_cuda(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     OBJ.mkdir(exist_ok=True)
     # this file is a dependency too: a changed flag in CUDA_UNITS must rebuild the unit
-    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "lgcu.h", Path(__file__)]
+    headers = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "lgcu.h", ROOT / "include" / "lgcu_interop.h", Path(__file__)]
     objs = []
     with open(LIB / "nvcc_ptxas.log", "a") as log:  # ptxas -v output (registers, spills) of the units compiled by this call; git-ignored
         for unit, extra in CUDA_UNITS.items():

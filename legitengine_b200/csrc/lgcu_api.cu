@@ -23,6 +23,19 @@ int fail(int status, const char *fmt, ...) {
   return status;
 }
 
+} // namespace
+
+// shared with lgcu_interop.cu (same thread-local message buffer behind lgcu_last_error); not part of the public ABI
+extern "C" __attribute__((visibility("hidden"))) int lgcu_set_last_error(int status, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_lastError, sizeof(g_lastError), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+namespace {
+
 int cudaStatus(cudaError_t e, const char *what) {
   if (e == cudaSuccess) return LGCU_OK;
   return fail(LGCU_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));

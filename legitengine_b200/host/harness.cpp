@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/lgcu_harness.h"
+#include "legit_cuda/ExternalImage.h" // compiled here so that the Vulkan hand-back wrappers stay buildable (no caller in the headless harness)
 #include "legit_cuda/InterleaveBuilder.h"
 #include "legit_cuda/SSVGIRenderer.h"
 

@@ -108,3 +108,9 @@ def scene_mesh(seed: int, n_boxes: int = DEFAULT_BOXES) -> Mesh:
     draws = np.zeros(nd.value, dtype=abi.DRAW_DTYPE)
     abi.check(lib.lgs_scene_mesh(seed, n_boxes, vertices.ctypes.data, indices.ctypes.data, draws.ctypes.data), "lgs_scene_mesh")
     return Mesh(vertices, indices, draws, scene_objects(seed, n_boxes))
+
+
+def load_packed_mesh(path) -> "Mesh":
+    """A mesh scene stored as .npz (vertices / indices / draws / objects as raw bytes of the include/lgcu.h structs) -> Mesh."""
+    z = np.load(path)
+    return Mesh(z["vertices"].view(abi.VERTEX_DTYPE).copy(), z["indices"].astype(np.uint32), z["draws"].view(abi.DRAW_DTYPE).copy(), z["objects"].view(abi.DRAW_CALL_DTYPE).copy())

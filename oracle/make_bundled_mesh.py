@@ -38,12 +38,9 @@ def main() -> None:
 
 def load():
     """-> legitengine_b200.scene.Mesh, or None when the file has not been generated."""
-    from legitengine_b200 import abi, scene
+    from legitengine_b200 import scene
 
-    if not OUT.exists():
-        return None
-    z = np.load(OUT)
-    return scene.Mesh(z["vertices"].view(abi.VERTEX_DTYPE).copy(), z["indices"].copy(), z["draws"].view(abi.DRAW_DTYPE).copy(), z["objects"].view(abi.DRAW_CALL_DTYPE).copy())
+    return scene.load_packed_mesh(OUT) if OUT.exists() else None
 
 
 if __name__ == "__main__":
