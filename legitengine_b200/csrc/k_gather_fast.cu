@@ -557,11 +557,12 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
   // neighbours in blockIdx.x, so they run at the same time and share the tile's pyramid neighbourhood through L2 (DRAM traffic stays at
   // 1.2x the algorithmic bytes). Whole 4K / 8K frames are indifferent to 4, 8 or 16 slices (1.348 / 1.346 / 1.354 ms at 4K; 5.05 / 5.08 /
   // 5.12 ms at 8K); grids of a few waves — a multi-GPU row strip, a 1080p frame — gain 4-5 % from 16 (one class per CTA: the shortest
-  // tail), r02q. Grids of fewer than ~6 waves of 64x64 tiles also use 64x32 tiles.
+  // tail), r02q.
   static const int envSlices = getenv("LGCU_GATHER_SLICES") ? atoi(getenv("LGCU_GATHER_SLICES")) : 0; // A/B switch: 1, 2, 4, 8 or 16
   const long long tileCount = (long long)tiles.x * tiles.y;
   const int kSlices = (envSlices == 1 || envSlices == 2 || envSlices == 4 || envSlices == 8 || envSlices == 16) ? envSlices : (tileCount < 10LL * smCount ? 16 : 4);
-  const bool smallTiles = (long long)tiles.x * tiles.y < 6LL * 4 * smCount;
+  static const int envTiles = getenv("LGCU_GATHER_SMALL_TILES") ? atoi(getenv("LGCU_GATHER_SMALL_TILES")) : -1; // A/B switch
+  const bool smallTiles = envTiles >= 0 ? envTiles != 0 : true; // 64x32 tiles of 128 threads everywhere: 8K whole frame 4.88 vs 5.04 ms with 64x64 / 256 threads (r02v)
   const dim3 gridBig(tiles.x * kSlices, tiles.y), gridSmall(tiles.x * kSlices, (rowsSpan + 31) / 32);
   // LGCU_GATHER_MINB: resident CTAs per SM the kernel is compiled for (A/B switch; 4 x 256 or 8 x 128 threads = 64 registers by default)
   static const int minb = getenv("LGCU_GATHER_MINB") ? atoi(getenv("LGCU_GATHER_MINB")) : 4;
@@ -579,8 +580,10 @@ cudaError_t launchGatherFast(const GatherArgs &a, const GatherTables &t, const v
     LGCU_LAUNCH_GATHER(true, 5, 10, false);
   else if (compact)
     LGCU_LAUNCH_GATHER(true, 4, 8, true);
-  else
+  else if (minb == 8)
     LGCU_LAUNCH_GATHER(true, 4, 8, false);
+  else // default: 9 resident CTAs of 128 threads (56 registers, 36 warps / SM: -1.7 % against 8 x 64 registers at 4K, r02v) or 4 of 256
+    LGCU_LAUNCH_GATHER(true, 4, 9, false);
 #undef LGCU_LAUNCH_GATHER
   return cudaGetLastError();
 }
