@@ -201,6 +201,7 @@ template <bool kSide, int kMinBlocks, int kT, bool kCompactWarp>
 __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_constant__ GatherArgs a, const __grid_constant__ FastTables tb,
                                                                           const float4 *__restrict__ side, int xSlices) {
   __shared__ uint4 sRow[kMaxSteps * kRowVecs];
+  __shared__ float4 sDir[kGatherDirs * 2];
   const int t = threadIdx.x;
   // tiles start on a multiple of 4 rows so that the pass number IS the pattern index (x&3) + 4*(y&3)   (:155, :161)
   // The 16 pattern classes of a tile are split over xSlices CTAs (0 or 1 = one CTA does all 16) that are neighbours in blockIdx.x
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
   for (int idx = idx0; idx < idx0 + idxPerCta; idx++) { // one pattern class per pass (CTA-uniform)
     __syncthreads(); // the previous pass is done with the staged rows
     for (int v = t; v < maxSteps * kRowVecs; v += kT) sRow[v] = reinterpret_cast<const uint4 *>(&tb.row[idx * kMaxSteps])[v];
+    if (t < kGatherDirs * 2) sDir[t] = reinterpret_cast<const float4 *>(&tb.dir[idx][0])[t];
     __syncthreads();
     const int x = tileX + tx + (idx & 3), y = tileY + ty + (idx >> 2);
     const bool active = x < a.indirect.w && y >= a.rows.y0 && y < a.rows.y1;
@@ -240,38 +242,36 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const V3 E = v3(__fadd_rn(cam.x, -C.x), __fadd_rn(cam.y, -C.y), __fadd_rn(cam.z, -C.z)); // cam - C
     const float invLenE = __fdiv_rn(1.0f, __fsqrt_rn(dot3Exact(E, E)));
     const V3 eye = v3(__fmul_rn(E.x, invLenE), __fmul_rn(E.y, invLenE), __fmul_rn(E.z, invLenE));
-    const float eN4 = 0.25f * dot3Exact(eye, N);
     // --- ray through the pixel: R0 ∝ far-plane point - cam --------------------------------------------------------------
     const V3 R0 = v3(fmaf(Ra.x, px, fmaf(Rb.x, py, Rc.x)), fmaf(Ra.y, px, fmaf(Rb.y, py, Rc.y)), fmaf(Ra.z, px, fmaf(Rb.z, py, Rc.z)));
     const float q0 = dotf(R0, R0);
-    const float n0 = sqrtf(q0);
+    const float n0 = q0 * fastRsqrt(q0);
+    const float eN = dot3Exact(eye, N), eN4 = 0.25f * eN;
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
     float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
-      const DirEntry de = tb.dir[idx][d];
-      const V3 Rd = v3(de.rdX, de.rdY, de.rdZ);
+      const float4 deA = sDir[2 * d], deB = sDir[2 * d + 1]; // {dirX, dirY, invDirX, invDirY}, {rdX, rdY, rdZ, q2}
+      const V3 Rd = v3(deB.x, deB.y, deB.z);
       // tangent = normalize(rayDir(p + dir) - rayDir(p)) in a cancellation-free form (:181-183)
-      float q2;
-      asm("mov.f32 %0, %1;" : "=f"(q2) : "f"(de.q2)); // opaque: keeps q2 in a register (the compiler otherwise re-reads it from the constant bank every march step)
-      const float q1 = 2.0f * dotf(R0, Rd);
-      const float n1 = sqrtf(q0 + q1 + q2);
+      const float q2 = deB.w, q1 = 2.0f * dotf(R0, Rd);
+      const float qs = q0 + q1 + q2, n1 = qs * fastRsqrt(qs);
       const float g = (q1 + q2) * fastRcp(n0 + n1);
       const V3 tanU = v3(fmaf(Rd.x, n0, -R0.x * g), fmaf(Rd.y, n0, -R0.y * g), fmaf(Rd.z, n0, -R0.z * g));
       const float tInv = tb.raySign * fastRsqrt(dotf(tanU, tanU));
       const V3 tang = v3(tanU.x * tInv, tanU.y * tInv, tanU.z * tInv);
-      const float tN4 = 0.25f * dotf(tang, N);
-      // initial horizon from the surface normal (:193-198)
-      const V3 bn = cross3(eye, tang); // -cross(tangent, eye)
-      const V3 q = cross3(bn, N);
-      float mx = dotf(q, eye), my = dotf(q, tang);
+      const float tN = dotf(tang, N), tN4 = 0.25f * tN;
+      // initial horizon from the surface normal (:193-198): q = cross(-cross(tangent, eye), N) = tangent (eye.N) - eye (tangent.N)
+      // for unit eye and tangent, so (q.eye, q.tangent) = (te eN - tN, eN - te tN) with te = tangent.eye
+      const float te = dotf(tang, eye);
+      float mx = fmaf(te, eN, -tN), my = fmaf(-te, tN, eN);
       float maxH = atan2Poly(my, mx);
       const float invM = fastRcp(fmaxf(fmaf(mx, mx, my * my), 1e-37f));
       float c2m = (mx * mx - my * my) * invM, s2m = 2.0f * mx * my * invM;
       // BoxRayCast + iteration count (:83-99, :202-212), exact like the strict kernel
-      const float t1 = __fmul_rn(0.0f - px, de.invDirX), t2 = __fmul_rn(vpx - px, de.invDirX);
-      const float t3 = __fmul_rn(0.0f - py, de.invDirY), t4 = __fmul_rn(vpy - py, de.invDirY);
+      const float t1 = __fmul_rn(0.0f - px, deA.z), t2 = __fmul_rn(vpx - px, deA.z);
+      const float t3 = __fmul_rn(0.0f - py, deA.w), t4 = __fmul_rn(vpy - py, deA.w);
       const float path = fabsf(glmMin(glmMax(t1, t2), glmMax(t3, t4)));
       int iterations = 0;
 #pragma unroll
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
       // per-direction affine coefficients of the horizon vector
       const float yE = dotf(tang, E), yR0 = tb.raySign * dotf(tang, R0);
       const float xRd = tb.raySign * dotf(eye, Rd), yRd = tb.raySign * dotf(tang, Rd);
-      const float dirX = de.dirX, dirY = de.dirY;
+      const float dirX = deA.x, dirY = deA.y;
 
       const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
       const uint4 *row = sRow;
