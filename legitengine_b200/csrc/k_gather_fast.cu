@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
     const float n0 = q0 * fastRsqrt(q0);
     const float eN = dot3Exact(eye, N), eN4 = 0.25f * eN;
     const float xE = dotf(eye, E), xR0 = tb.raySign * dotf(eye, R0);
-    float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f;
+    // out = sum over directions of (2 L_d) / 4 (:268) with L_d = sum(Ls*c) - 0.01*sum(c) + 0.01*hc0 (:209, :261-262): the light terms go
+    // straight into the pixel's sums (weight 0.5 c), the sum(c) and hc0 terms into one scalar for all four directions
+    float sumX = 0.0f, sumY = 0.0f, sumZ = 0.0f, cSum = 0.0f;
 
 #pragma unroll 1
     for (int d = 0; d < kGatherDirs; d++) {
@@ -282,12 +284,10 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
       }
       if (!active) iterations = 0;
       // ambient term 0.01 * HC(0, maxH) (:209): cos(0) = 1, sin(0) = 0.  L = sum(Ls*c) - 0.01*sum(c) + 0.01*hc0
-      float Lx = 0.0f, Ly = 0.0f, Lz = 0.0f;
-      float cSum = -(eN4 * (1.0f - c2m) + tN4 * (2.0f * maxH - s2m));
+      cSum -= eN4 * (1.0f - c2m) + tN4 * (2.0f * maxH - s2m);
       // per-direction affine coefficients of the horizon vector
       const float yE = dotf(tang, E), yR0 = tb.raySign * dotf(tang, R0);
       const float xRd = tb.raySign * dotf(eye, Rd), yRd = tb.raySign * dotf(tang, Rd);
-      const float dirX = deA.x, dirY = deA.y;
 
       const int warpIters = __reduce_max_sync(0xffffffffu, iterations);
       const uint4 *row = sRow;
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
       for (int k = 0; k < warpIters; k++, row += kRowVecs) { // :214
         const float4 hdr = *reinterpret_cast<const float4 *>(row); // off, frac, l0, l1
         const float off = hdr.x, frac = hdr.y;
-        const float sx = fmaf(dirX, off, px), sy = fmaf(dirY, off, py); // :218-219 (in pixels)
-        const int4 qa = *reinterpret_cast<const int4 *>(row + 2);
+        const float2 dir = *reinterpret_cast<const float2 *>(&sDir[2 * d]); // re-read per step: two registers less across the loop
+        const float sx = fmaf(dir.x, off, px), sy = fmaf(dir.y, off, py); // :218-219 (in pixels)
         const Footprint f0 = footprint(*reinterpret_cast<const float4 *>(row + 1), sx, sy);
-        float z = fetchDepth<kSide>(qa, row + 3, f0, pyr);
+        float z = fetchDepth<kSide>(*reinterpret_cast<const int4 *>(row + 2), row + 3, f0, pyr);
         Footprint f1; // only set and only read when tri
         const bool tri = frac > 0.0f; // the same for every thread of the CTA
         if (tri) {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           // product of the four saturates of :220-228 (at most one per axis is below 1): sat(min(u, 1 - u) * 10)
           const float ex = fminf(sx, vpx - sx) * invVpx10, ey = fminf(sy, vpy - sy) * invVpy10;
           const float sideMult = saturatef(ex) * saturatef(ey);
-          float3 ls = fetchLight(qa, row + 3, f0, pyr); // :256
+          float3 ls = fetchLight(*reinterpret_cast<const int4 *>(row + 2), row + 3, f0, pyr); // :256
           if (tri) {
             const float3 hi = fetchLight(*reinterpret_cast<const int4 *>(row + 5), row + 6, f1, pyr);
             ls.x = fmaf(frac, hi.x - ls.x, ls.x);
@@ -328,9 +328,10 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
             ls.z = fmaf(frac, hi.z - ls.z, ls.z);
           }
           const float c = hc * sideMult; // :258
-          Lx = fmaf(ls.x, c, Lx);        // :261
-          Ly = fmaf(ls.y, c, Ly);
-          Lz = fmaf(ls.z, c, Lz);
+          const float ch = 0.5f * c;
+          sumX = fmaf(ls.x, ch, sumX);   // :261, :268
+          sumY = fmaf(ls.y, ch, sumY);
+          sumZ = fmaf(ls.z, ch, sumZ);
           cSum += c;                     // :262
           maxH = h;                      // :263
           c2m = c2;
@@ -339,12 +340,9 @@ __global__ void __launch_bounds__(kT, kMinBlocks) gatherFastKernel(const __grid_
           my = hy;
         }
       }
-      const float amb = -0.01f * cSum;
-      sumX = fmaf(0.5f, Lx + amb, sumX); // :268
-      sumY = fmaf(0.5f, Ly + amb, sumY);
-      sumZ = fmaf(0.5f, Lz + amb, sumZ);
     }
-    if (active) storeColor(a.outFormat, a.indirect, x, y, make_float4(sumX, sumY, sumZ, 1.0f)); // :270
+    const float amb = -0.005f * cSum;
+    if (active) storeColor(a.outFormat, a.indirect, x, y, make_float4(sumX + amb, sumY + amb, sumZ + amb, 1.0f)); // :270
   }
 }
 
