@@ -613,18 +613,34 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     with torch.cuda.stream(stream):
         sr, frag_host, full_view_ptr = build(bounds)
         # cost-aware strips (sharding.rebalance_bounds): measure every rank's own kernel time, move the boundaries, rebuild
-        for _ in range(args.balance if args.transport == "p2p" else 0):
-            prof = stage_profile(sr, frames=4)
-            own = [prof["front"][r] + prof["chains"][r] + prof["gather_final"][r] for r in range(world)]
-            new_bounds = sharding.rebalance_bounds(bounds, own, H)
+        # cost-aware strips: measure every rank's own kernel time, refine the frame's per-block cost profile with it
+        # (sharding.refine_cost_density), cut the profile into equal parts, rebuild; in the end keep the partition whose slowest rank was
+        # fastest (the un-captured stage profile is noisy at the +-2 % level, so the last partition tried is not always the best one)
+        density, tried = None, []
+        for it in range((args.balance + 1) if args.transport == "p2p" else 0):
+            prof = stage_profile(sr, frames=10)
+            # what a rank adds to the frame's critical path: everyone waits for the slowest front and chains stage anyway (level 4 of the
+            # chains is gathered from every rank), so it is the gather + final stage that has to be equal; the front only counts through its
+            # share of the slowest rank's stage
+            own = [prof["gather_final"][r] + 0.25 * prof["front"][r] for r in range(world)]
             balance_log.append({"bounds": bounds, "own_ms": [round(v, 4) for v in own]})
+            tried.append((max(own), bounds))
+            if it == args.balance:
+                new_bounds = min(tried)[1]  # last round: go back to the best partition seen
+            else:
+                density = sharding.refine_cost_density(density, bounds, own, H)
+                new_bounds = sharding.bounds_from_density(density, world, H)
             if new_bounds == bounds:
-                break
+                if it == args.balance or min(tried)[1] == bounds:
+                    break
+                new_bounds = min(tried)[1]
             torch.cuda.synchronize()
             sr.close()
             del frag_host
             bounds = new_bounds
             sr, frag_host, full_view_ptr = build(bounds)
+            if it == args.balance:
+                break
 
         def barrier():
             dist.barrier()

@@ -96,6 +96,46 @@ def rebalance_bounds(bounds: Sequence[Tuple[int, int]], costs: Sequence[float], 
     return [(min(cuts[r] * granule, height), min(cuts[r + 1] * granule, height)) for r in range(world)]
 
 
+def refine_cost_density(density: Sequence[float] | None, bounds: Sequence[Tuple[int, int]], costs: Sequence[float], height: int,
+                        granule: int = GRANULE) -> List[float]:
+    """One step of learning the frame's cost per granule block from per-strip measurements: inside every strip the current estimate
+    (uniform at first) is scaled so that the strip's total equals its measured cost. The shape an earlier partition taught survives
+    inside the strips of the next one, so a few measure -> cut rounds with DIFFERENT boundaries converge on the real profile instead of
+    re-flattening it every round (which is what `rebalance_bounds` alone does and why it stalls at a +-6 % spread on 8 strips)."""
+    blocks = (height + granule - 1) // granule
+    d = [1.0] * blocks if density is None else list(density)
+    for (y0, y1), c in zip(bounds, costs):
+        if y1 <= y0 or not c > 0.0:
+            continue
+        idx = range(y0 // granule, (y1 + granule - 1) // granule)
+        cur = sum(d[b] for b in idx)
+        if cur > 0.0:
+            k = c / cur
+            for b in idx:
+                d[b] *= k
+    return d
+
+
+def bounds_from_density(density: Sequence[float], world: int, height: int, granule: int = GRANULE) -> List[Tuple[int, int]]:
+    """Strip boundaries that cut the cumulative block cost into `world` equal parts (block granularity, at least one block per rank)."""
+    blocks = len(density)
+    if world == 1 or blocks <= world:
+        return strip_bounds(height, world)
+    total = sum(density)
+    cuts, acc, b = [0], 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while b < blocks and acc + density[b] * 0.5 < target:
+            acc += density[b]
+            b += 1
+        cut = min(max(b, cuts[-1] + 1), blocks - (world - r))
+        cuts.append(cut)
+        if cut != b:
+            acc, b = sum(density[:cut]), cut
+    cuts.append(blocks)
+    return [(min(cuts[r] * granule, height), min(cuts[r + 1] * granule, height)) for r in range(world)]
+
+
 def level_height(height: int, level: int) -> int:
     return height >> level
 
