@@ -311,6 +311,22 @@ int lgcu_frame_counter_bump(uint32_t *frameCounter, void *stream);
 int lgcu_signal_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, void *stream);
 /* Blocks the stream (a one-warp spinning kernel) until *flags[i] >= *frameCounter - lag for every i < count. */
 int lgcu_wait_flags(uint32_t *const *flags, uint32_t count, const uint32_t *frameCounter, uint32_t lag, void *stream);
+/* One exchange step of the strip protocol in ONE launch — signal, wait, pull and acknowledge fused with the copy over peer memory:
+ *   bump != 0        : *frameCounter += 1 first (then no copies are allowed: the step opens a frame)
+ *   signalBefore     : flags set to the frame number before anything else ("my previous stage is done")
+ *   wait, lag        : every CTA spins until the flags reach frame - lag, then
+ *   copies           : the slabs are pulled (or pushed) by the whole grid, and
+ *   signalAfter      : the LAST CTA to finish sets these flags ("I am done reading your rows"); doneCounter is a zero-initialised
+ *                      device word owned by the caller that the kernel uses to find that CTA (it leaves it at zero).
+ * Lists hold at most 32 flags / 64 slabs. Replaces a sequence of up to four of the calls above (and their launch gaps). */
+typedef struct lgcu_exchange_desc {
+  uint32_t *const *signalBefore; uint32_t signalBeforeCount;
+  uint32_t *const *wait; uint32_t waitCount; uint32_t lag;
+  const lgcu_row_copy *copies; uint32_t copyCount;
+  uint32_t *const *signalAfter; uint32_t signalAfterCount;
+  uint32_t *frameCounter; uint32_t *doneCounter; uint32_t bump;
+} lgcu_exchange_desc;
+int lgcu_exchange(const lgcu_exchange_desc *desc, void *stream);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,13 @@ class RowCopy(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("bytes", C.c_uint64)]
 
 
+class ExchangeDesc(C.Structure):
+    """lgcu_exchange_desc (include/lgcu.h): one fused exchange step of the strip protocol."""
+    _fields_ = [("signalBefore", C.POINTER(C.c_void_p)), ("signalBeforeCount", C.c_uint32), ("wait", C.POINTER(C.c_void_p)), ("waitCount", C.c_uint32),
+                ("lag", C.c_uint32), ("copies", C.POINTER(RowCopy)), ("copyCount", C.c_uint32), ("signalAfter", C.POINTER(C.c_void_p)),
+                ("signalAfterCount", C.c_uint32), ("frameCounter", C.c_void_p), ("doneCounter", C.c_void_p), ("bump", C.c_uint32)]
+
+
 class ClearValues(C.Structure):
     _fields_ = [("color", C.c_float * 4), ("depth", C.c_float)]
 
@@ -195,7 +202,8 @@ def load_lgcu() -> C.CDLL:
         lib.lgcu_frame_counter_bump.argtypes = [C.c_void_p, C.c_void_p]
         lib.lgcu_signal_flags.argtypes = [P(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]
         lib.lgcu_wait_flags.argtypes = [P(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
-        for fn in (lib.lgcu_copy_rows, lib.lgcu_frame_counter_bump, lib.lgcu_signal_flags, lib.lgcu_wait_flags):
+        lib.lgcu_exchange.argtypes = [P(ExchangeDesc), C.c_void_p]
+        for fn in (lib.lgcu_copy_rows, lib.lgcu_frame_counter_bump, lib.lgcu_signal_flags, lib.lgcu_wait_flags, lib.lgcu_exchange):
             fn.restype = C.c_int
         lib.lgcu_gather_scratch_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         lib.lgcu_gather_scratch_bytes.restype = C.c_uint64

@@ -51,6 +51,8 @@ cudaError_t launchMipBlurChain(const ChainArgs &a, cudaStream_t s) {
 // instead of 64), each output summed in the shader's order (x outer, y inner, sequential fp32) so the result is bit-exact.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 namespace lgcu {
 namespace {
 
@@ -145,6 +147,56 @@ __global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kChainThr
     chainTail<kRG32>(a, a.moments, a.blurredMoments, ctaRank);
 }
 
+// A/B variant of the blur grid (LGCU_BLUR_SMEM=1): the CTA's 32 x 32 output tile and its halo (window -R..R-1: 35 x 35 texels for
+// R = 2) are staged in shared memory with coalesced loads, and the register windows are filled from there. Measured against the
+// direct version below (whose overlapping window loads are served by L1): see profiles/README.md, round 2.
+template <uint32_t F, int R> __device__ __forceinline__ void blurTileStaged(uint2 (*tile)[kBlurTileW + 2 * R], const LevelView &src, const LevelView &dst, int x0, int y0,
+                                                                              int rowEnd) {
+  constexpr int kW = kBlurTileW + 2 * R - 1, kH = kBlurTileH + 2 * R - 1; // texels the tile's windows touch
+  for (int i = threadIdx.x; i < kW * kH; i += kChainThreads) {
+    const int tx = i % kW, ty = i / kW;
+    tile[ty][tx] = loadTexel<false>(src, clampi(x0 + tx - R, 0, src.w - 1), clampi(y0 + ty - R, 0, src.h - 1));
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = (threadIdx.x >> 5) * kBlurRowsPerThread;
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= src.w || y >= rowEnd) return;
+  const int rows = min(kBlurRowsPerThread, rowEnd - y);
+  constexpr int kWin = 2 * R;
+#pragma unroll
+  for (int o = 0; o < kBlurRowsPerThread; o++) {
+    if (o >= rows) break;
+    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float totalWeight = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kWin; i++)
+#pragma unroll
+      for (int j = 0; j < kWin; j++) {
+        const float4 v = Texel<F>::unpack(tile[ly + o + j][lx + i]);
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        totalWeight += 1.0f;
+      }
+    Texel<F>::store(dst, x, y + o, make_float4(sum.x / totalWeight, sum.y / totalWeight, sum.z / totalWeight, sum.w / totalWeight));
+  }
+}
+
+__global__ void __launch_bounds__(kChainThreads) frameChainsStagedKernel(const __grid_constant__ ChainsLaunch p) {
+  __shared__ uint2 tile[kBlurTileH + 3][kBlurTileW + 4];
+  const ChainsArgs &a = p.a;
+  int b = blockIdx.x;
+  const int chain = b >= p.blockBegin[1][0] ? 1 : 0;
+  int l = 1;
+  while (l < a.gridLevels && b >= p.blockBegin[chain][l]) l++;
+  b -= p.blockBegin[chain][l - 1];
+  const LevelView &src = chain ? a.moments.lv[l] : a.light.lv[l], &dst = chain ? a.blurredMoments.lv[l] : a.blurredLight.lv[l];
+  const int bx = (src.w + kBlurTileW - 1) / kBlurTileW;
+  const int x0 = (b % bx) * kBlurTileW, y0 = p.rowBegin[l - 1] + (b / bx) * kBlurTileH;
+  if (chain)
+    blurTileStaged<kRG32, 2>(tile, src, dst, x0, y0, p.rowEnd[l - 1]);
+  else
+    blurTileStaged<kF16, 2>(tile, src, dst, x0, y0, p.rowEnd[l - 1]);
+}
+
 __global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_constant__ ChainsLaunch p) {
   const ChainsArgs &a = p.a;
   int b = blockIdx.x;
@@ -187,7 +239,11 @@ cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s) {
   // data-independent and could overlap (programmatic dependent launch, or the tail as the first clusters of one grid); at 1 % of the
   // frame that has not been worth a second synchronisation scheme yet.
   if (a.levels > a.gridLevels + 1) chainTailKernel<<<2 * kTailCluster, kChainThreads, 0, s>>>(a);
-  if (blocks > 0) frameChainsKernel<<<blocks, kChainThreads, 0, s>>>(p);
+  static const bool staged = getenv("LGCU_BLUR_SMEM") && atoi(getenv("LGCU_BLUR_SMEM")) != 0; // A/B switch (radius 2 only)
+  if (blocks > 0 && staged && a.radius == 2)
+    frameChainsStagedKernel<<<blocks, kChainThreads, 0, s>>>(p);
+  else if (blocks > 0)
+    frameChainsKernel<<<blocks, kChainThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -649,6 +649,34 @@ static bool fillFlags(uint32_t *const *flags, uint32_t count, FlagArgs *a) {
   return true;
 }
 
+int lgcu_exchange(const lgcu_exchange_desc *d, void *stream) {
+  if (!d || !d->frameCounter) return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: null descriptor / frame counter");
+  ExchangeArgs a;
+  if (!fillFlags(d->signalBefore, d->signalBeforeCount, &a.signalBefore) || !fillFlags(d->wait, d->waitCount, &a.wait) || !fillFlags(d->signalAfter, d->signalAfterCount, &a.signalAfter))
+    return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: bad flag list (max %d)", kMaxFlags);
+  if (d->copyCount > (uint32_t)kMaxCopies || (!d->copies && d->copyCount)) return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: at most %d slabs per step", kMaxCopies);
+  if (d->bump && d->copyCount) return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: the step that bumps the frame counter cannot copy (single CTA)");
+  if (d->signalAfterCount && !d->doneCounter) return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: signalAfter needs a doneCounter");
+  a.copies.count = 0;
+  uint64_t units = 0;
+  for (uint32_t i = 0; i < d->copyCount; i++) {
+    const lgcu_row_copy &c = d->copies[i];
+    if (!c.bytes) continue;
+    if (!c.src || !c.dst || (c.bytes % 16) != 0 || (reinterpret_cast<uintptr_t>(c.src) % 16) != 0 || (reinterpret_cast<uintptr_t>(c.dst) % 16) != 0)
+      return fail(LGCU_ERR_INVALID_ARGUMENT, "exchange: slab %u must be non-null, 16-byte aligned and a multiple of 16 bytes", i);
+    units += c.bytes / 16;
+    a.copies.src[a.copies.count] = c.src;
+    a.copies.dst[a.copies.count] = c.dst;
+    a.copies.unitEnd[a.copies.count] = units;
+    a.copies.count++;
+  }
+  a.frame = d->frameCounter;
+  a.done = d->doneCounter;
+  a.lag = (int)d->lag;
+  a.bump = d->bump ? 1 : 0;
+  return cudaStatus(launchExchange(a, smCountOfCurrentDevice(), static_cast<cudaStream_t>(stream)), "exchange");
+}
+
 int lgcu_frame_counter_bump(uint32_t *frameCounter, void *stream) {
   if (!frameCounter) return fail(LGCU_ERR_INVALID_ARGUMENT, "frame_counter_bump: null counter");
   return cudaStatus(launchBumpFrame(frameCounter, static_cast<cudaStream_t>(stream)), "frame_counter_bump");

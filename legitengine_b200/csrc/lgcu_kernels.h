@@ -168,6 +168,13 @@ struct FlagArgs {
   uint32_t *flags[kMaxFlags];
   int count;
 };
+struct ExchangeArgs { // one fused exchange step: signalBefore -> wait -> copies -> (last CTA) signalAfter
+  FlagArgs signalBefore, wait, signalAfter;
+  RowCopyArgs copies;
+  uint32_t *frame, *done;
+  int lag, bump;
+};
+cudaError_t launchExchange(const ExchangeArgs &a, int smCount, cudaStream_t s);
 cudaError_t launchRowCopies(const RowCopyArgs &a, int smCount, cudaStream_t s);
 cudaError_t launchBumpFrame(uint32_t *frame, cudaStream_t s);
 cudaError_t launchSignal(const FlagArgs &a, const uint32_t *frame, cudaStream_t s);

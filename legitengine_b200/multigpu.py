@@ -149,7 +149,7 @@ class P2PStripRenderer(StripRenderer):
 
     FRONT, CHAINS, DELIVERED, ACK, FREE = range(5)
 
-    def __init__(self, *args, direct_present: bool = True, **kwargs):
+    def __init__(self, *args, direct_present: bool = True, fused_exchange: bool = True, **kwargs):
         stream = kwargs.get("stream")
         if not stream:
             raise ValueError("P2PStripRenderer needs an explicit CUDA stream, passed as stream=... (the same one the harness renders on)")
@@ -157,6 +157,9 @@ class P2PStripRenderer(StripRenderer):
         self._lgcu = abi.load_lgcu()
         self._stream = C.c_void_p(stream)
         self._direct_present = direct_present
+        # fused_exchange: every exchange step (signal -> wait -> pull -> acknowledge) is ONE kernel (lgcu_exchange) instead of up to four
+        # launches; needs the composite without a copy (the separate push keeps the unfused sequence)
+        self._fused = fused_exchange and direct_present
         self._ready = False
         self._peer_ptrs: List[int] = []
 
@@ -232,6 +235,30 @@ class P2PStripRenderer(StripRenderer):
         self._sig_delivered = flag_list(self.DELIVERED, {self.root}, rank) if self._is_pusher else ((C.c_void_p * 1)(), 0)
         self._wait_delivered = local_flags(self.DELIVERED, pushers) if rank == self.root else ((C.c_void_p * 1)(), 0)
         self.received_bytes = sum(c.bytes for c in self._pull_chains[0][: self._pull_chains[1]]) + sum(c.bytes for c in self._pull_gather[0][: self._pull_gather[1]])
+        if self._fused:
+            if max(self._pull_chains[1], self._pull_gather[1]) > 64:
+                self._fused = False  # more slabs than one exchange launch takes: keep the chunked copies
+            else:
+                done = self._flags + 4 * (5 * world + 1)  # a zero-initialised word after the frame counter
+
+                def step(sig_before=None, wait=None, lag=0, copies=None, sig_after=None, bump=False):
+                    none_f, none_c = ((C.c_void_p * 1)(), 0), ((abi.RowCopy * 1)(), 0)
+                    sb, w, cp, sa = sig_before or none_f, wait or none_f, copies or none_c, sig_after or none_f
+                    return abi.ExchangeDesc(sb[0], sb[1], w[0], w[1], lag, cp[0], cp[1], sa[0], sa[1], self._counter, C.c_void_p(done), 1 if bump else 0), (sb, w, cp, sa)
+
+                def merged(a, b):
+                    ptrs = list(a[0][: a[1]]) + list(b[0][: b[1]])
+                    return (C.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
+
+                free_wait = self._wait_free if self._is_pusher else ((C.c_void_p * 1)(), 0)
+                self._steps = {
+                    "open": step(sig_before=self._sig_free, wait=self._wait_ack, lag=1, bump=True),
+                    "front": step(sig_before=self._sig_front, wait=self._wait_front, copies=self._pull_chains),
+                    # FREE is waited for here, together with the CHAINS flags: it has to precede gather + final, which writes the strip into
+                    # the presenting GPU's image
+                    "chains": step(sig_before=self._sig_chains, wait=merged(self._wait_chains, free_wait), copies=self._pull_gather, sig_after=self._sig_ack),
+                    "close": step(sig_before=self._sig_delivered, wait=self._wait_delivered),
+                }
         torch.cuda.synchronize()
         dist.barrier()
         self._ready = True
@@ -265,6 +292,8 @@ class P2PStripRenderer(StripRenderer):
                 ev.record()
                 marks.append(ev)
 
+        if self._fused:
+            return self._render_fused(gi_flags, mark)
         abi.check(self._lgcu.lgcu_frame_counter_bump(self._counter, self._stream), "lgcu_frame_counter_bump")
         self._signal(self._sig_free)
         self._wait(self._wait_ack, lag=1)
@@ -296,6 +325,32 @@ class P2PStripRenderer(StripRenderer):
                 self._copy(self._push)
             self._signal(self._sig_delivered)
         self._wait(self._wait_delivered)
+        mark()
+
+    def _exchange(self, name: str) -> None:
+        desc, _keepalive = self._steps[name]
+        abi.check(self._lgcu.lgcu_exchange(C.byref(desc), self._stream), "lgcu_exchange")
+
+    def _render_fused(self, gi_flags: int, mark) -> None:
+        """The frame with every exchange step as one launch: open | front | exchange | chains | exchange | gather + final | close."""
+        r, rows = self.renderer, self.rows
+        have = rows[1] > rows[0]
+        self._exchange("open")    # bump F, root: signal FREE, wait ACK >= F-1
+        mark()
+        if have:
+            r.render_stages(harness.STAGE_FRONT, rows, gi_flags=gi_flags)
+        mark()
+        self._exchange("front")   # signal FRONT, wait FRONT, pull chain halos
+        mark()
+        if have:
+            r.render_stages(harness.STAGE_CHAINS, rows, gi_flags=gi_flags)
+        mark()
+        self._exchange("chains")  # signal CHAINS, wait CHAINS (+ FREE), pull gather halos, last CTA: signal ACK
+        mark()
+        if have:
+            r.render_stages(harness.STAGE_GATHER | harness.STAGE_FINAL, rows, gi_flags=gi_flags)
+        mark()
+        self._exchange("close")   # pushers: signal DELIVERED; root: wait DELIVERED
         mark()
 
     def capture(self, gi_flags: int = abi.GI_DEFAULT) -> None:

@@ -53,10 +53,11 @@ def _program(rank, info, root, frames, ack_wait=True, direct_present=False):
         ops.append(("work", "chains", [(rank, "chain"), (rank, "chain_halo")], [(rank, "blurred")]))
         ops.append(("signal", CHAINS, me["gather_pullers"]))
         ops.append(("wait", CHAINS, me["gather_sources"], 0))
+        if direct_present and me["pusher"]:  # fused exchange: FREE is waited for together with the CHAINS flags, before the pull
+            ops.append(("wait", FREE, {root}, 0))
         ops.append(("work", "pull_gather", [(s, "blurred") for s in me["gather_sources"]] + [(s, "blurred0") for s in me["gather_sources"]], [(rank, "blurred_halo")]))
         ops.append(("signal", ACK, me["chain_sources"] | me["gather_sources"]))
         if direct_present and me["pusher"]:  # the final pass writes the strip straight into the root's swapchain image
-            ops.append(("wait", FREE, {root}, 0))
             ops.append(("work", "gather_final", [(rank, "blurred"), (rank, "blurred0"), (rank, "blurred_halo")], [(root, f"swap_from_{rank}")]))
             ops.append(("signal", DELIVERED, {root}))
         else:
