@@ -76,6 +76,9 @@ def parse_args():
                     help="strips: what every rank starts from — its strip of the pre-rasterised fragment buffer (uploaded per frame in the e2e leg), or the "
                          "mesh scene, which every rank rasterises for its own rows on the device (ShadowPass + GBufferRasterPass with lgcu_rows)")
     ap.add_argument("--balance", type=int, default=5, help="strips (p2p): up to this many measure -> rebalance rounds of the strip boundaries (0 = equal rows)")
+    ap.add_argument("--strip-bounds", default=None, help="strips: fixed boundaries y0,y1,...,yN (multiples of 16) instead of measuring and re-balancing")
+    ap.add_argument("--unfused-exchange", action="store_true", help="strips (p2p): separate signal / wait / copy launches instead of one lgcu_exchange kernel per step (A/B)")
+    ap.add_argument("--skip-extras", action="store_true", help="strips: skip the single-GPU / replica / batch legs (A/B runs)")
     ap.add_argument("--no-graph", action="store_true", help="strips: launch stages and NCCL transfers from Python every frame instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -583,7 +586,8 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         frags = frag_host.numpy().view(abi.FRAGMENT_DTYPE).reshape(-1, W)
         if mesh is None:
             scene.scene_fragments(seed, W, H, m, rows=(y0, y1), out=_OffsetRows(frags, y0))
-        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present, bounds=bounds)
+        extra = {"fused_exchange": not args.unfused_exchange} if args.transport == "p2p" else {}
+        sr = cls(W, H, rank, world, dist, stream=stream.cuda_stream, present=not args.no_present, bounds=bounds, **extra)
         sr.renderer.upload_objects(objects.ctypes.data, len(objects))
         sr.renderer.upload_light_depth(shadow.data_ptr(), 1024)
         ptr = frag_host.data_ptr() - y0 * W * 32  # lgh_upload_fragments takes the address of row 0
@@ -596,19 +600,25 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     def stage_profile(sr, frames=8):
         """Per-rank GPU time between the stage marks of un-captured frames, all-gathered: {stage: [ms of rank 0, 1, ...]}."""
         n_marks = len(sr.STAGE_MARKS)
-        acc = torch.zeros(n_marks - 1, device="cuda")
+        samples = []
         for i in range(frames + 2):
             marks = []
             sr.render(gi_flags, marks=marks)
             torch.cuda.synchronize()
             if i >= 2:
-                acc += torch.tensor([marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks - 1)], device="cuda") / frames
+                samples.append([marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks - 1)])
+        acc = torch.tensor(np.median(np.asarray(samples), axis=0), device="cuda", dtype=torch.float32)  # median: robust against launch jitter
         dist.barrier()
         every = [torch.zeros_like(acc) for _ in range(world)]
         dist.all_gather(every, acc)
         return {name: [round(float(e[j]), 4) for e in every] for j, name in enumerate(sr.STAGE_MARKS[1:])}
 
     bounds = sharding.strip_bounds(H, world)
+    if args.strip_bounds:
+        cuts = [int(v) for v in args.strip_bounds.split(",")]
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == H, "--strip-bounds needs world+1 increasing cuts from 0 to the height"
+        bounds = [(cuts[i], cuts[i + 1]) for i in range(world)]
+        args.balance = -1
     balance_log = []
     with torch.cuda.stream(stream):
         sr, frag_host, full_view_ptr = build(bounds)
@@ -617,7 +627,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         # (sharding.refine_cost_density), cut the profile into equal parts, rebuild; in the end keep the partition whose slowest rank was
         # fastest (the un-captured stage profile is noisy at the +-2 % level, so the last partition tried is not always the best one)
         density, tried = None, []
-        for it in range((args.balance + 1) if args.transport == "p2p" else 0):
+        for it in range((args.balance + 1) if (args.transport == "p2p" and args.balance >= 0) else 0):
             prof = stage_profile(sr, frames=10)
             # what a rank adds to the frame's critical path: everyone waits for the slowest front and chains stage anyway (level 4 of the
             # chains is gathered from every rank), so it is the gather + final stage that has to be equal; the front only counts through its
@@ -704,6 +714,16 @@ def run_strips(args, rank: int, world: int, local_rank: int):
     extra_steps = max(10, min(args.steps, 50))
     torch.cuda.synchronize()
     dist.barrier()
+    if args.skip_extras:
+        if rank == 0:
+            print(json.dumps({"ms_per_step": ms_per_step, "value": W * H / (ms_per_step * 1e-3) / 1e6, "n_gpus": world, "strips": bounds, "fused_exchange": not args.unfused_exchange,
+                              "stage_ms_per_rank": stage_ms}), flush=True)
+        torch.cuda.synchronize()
+        sr.release_graph()
+        dist.barrier()
+        sr.close()
+        dist.destroy_process_group()
+        return
     single_ms = resident_frame_ms(W, H, seed, extra_steps, gi_flags=gi_flags) if rank == 0 else 0.0
     dist.barrier()
     rw, rh = WORKLOADS["4k"]
