@@ -182,3 +182,41 @@ def test_rebalance_bounds_equalises_measured_cost():
     assert sharding.rebalance_bounds(tiny, [1.0] * 8, 48) == tiny
     skew = sharding.rebalance_bounds(sharding.strip_bounds(256, 4), [100.0, 1.0, 1.0, 1.0], 256)
     assert all(y1 - y0 >= sharding.GRANULE for y0, y1 in skew) and skew[0][1] < 64
+
+
+def test_cost_profile_is_learnt_across_rebalancing_rounds():
+    """sharding.refine_cost_density + bounds_from_density (bench.py's re-balancing): per-strip measurements of DIFFERENT partitions refine
+    one per-block cost profile; the partitions converge on equal cost, stay on the 16-row grid, cover the frame, keep every rank non-empty,
+    and a profile with a sharp expensive band (the horizon rows of the synthetic frame) ends within a few per cent of balance."""
+    import math
+
+    H, world = 4320, 8
+    blocks = H // sharding.GRANULE
+    true = [1.0 + 0.4 * math.sin(b / 25.0) + (1.5 if 128 <= b < 140 else 0.0) for b in range(blocks)]
+
+    def measure(bounds):
+        return [sum(true[y0 // 16:(y1 + 15) // 16]) for y0, y1 in bounds]
+
+    bounds, density, spreads = sharding.strip_bounds(H, world), None, []
+    for _ in range(6):
+        costs = measure(bounds)
+        spreads.append(max(costs) / (sum(costs) / world))
+        density = sharding.refine_cost_density(density, bounds, costs, H)
+        assert len(density) == blocks and all(d > 0 for d in density)
+        bounds = sharding.bounds_from_density(density, world, H)
+        assert bounds[0][0] == 0 and bounds[-1][1] == H
+        assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:])) and all(y1 > y0 and y0 % 16 == 0 for y0, y1 in bounds)
+    # (with a 16-row granule and a sharp band the last rounds hop between two neighbouring partitions: bench.py keeps the best one measured)
+    assert spreads[0] > 1.15 and min(spreads) < 1.04 and max(spreads[1:]) < 1.06, spreads
+    # the profile keeps what an earlier partition taught: after the rounds its shape correlates with the true one inside a strip too
+    y0, y1 = bounds[2]
+    seg = slice(y0 // 16, y1 // 16)
+    est, tru = density[seg], true[seg]
+    me, mt = sum(est) / len(est), sum(tru) / len(tru)
+    cov = sum((a - me) * (b - mt) for a, b in zip(est, tru))
+    assert cov >= 0.0
+    # degenerate inputs: one rank, more ranks than blocks, a rank with an empty strip and no cost
+    assert sharding.bounds_from_density([1.0] * 4, 1, 64) == [(0, 64)]
+    assert sharding.bounds_from_density([1.0] * 2, 4, 32) == sharding.strip_bounds(32, 4)
+    d = sharding.refine_cost_density(None, [(0, 32), (32, 32)], [2.0, 0.0], 32)
+    assert d == [1.0, 1.0]
