@@ -316,8 +316,11 @@ __device__ __forceinline__ void resolveFragment(const RasterKernelArgs &A, unsig
 }
 
 // One warp per 32x16 screen tile; lane = column. kFragments: G-buffer target (fragment buffer) / depth-only target (shadow map).
+// 8 resident CTAs per SM (64 registers, some spills): the kernel is bound by the latency of its fp64 chains, not by their throughput
+// (ncu r03c: fp64 pipe 27 %, issue 34 % at 126 registers / 4 CTAs), so occupancy buys more than the spills cost — 4K G-buffer pass
+// 0.261 ms at 4 CTAs, 0.237 at 5, 0.228 at 6, 0.214 at 8 and at 10.
 template <bool kFragments>
-__global__ void __launch_bounds__(128) rasterTileKernel(const __grid_constant__ RasterKernelArgs A, lgcu_fragment *fragments, uint64_t pitch, LevelView depth) {
+__global__ void __launch_bounds__(128, 8) rasterTileKernel(const __grid_constant__ RasterKernelArgs A, lgcu_fragment *fragments, uint64_t pitch, LevelView depth) {
   const int lane = threadIdx.x & 31;
   const int tilesX = (A.width + kScreenTileW - 1) / kScreenTileW;
   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
