@@ -16,6 +16,7 @@ import torch  # noqa: E402
 from legitengine_b200 import abi, harness, scene  # noqa: E402
 
 GI = abi.GI_STRICT if os.environ.get("LGCU_PASS_TIMES_STRICT") else abi.GI_DEFAULT  # shader-order gather kernel (ncu: algorithmic FP32 count)
+RADIUS = int(os.environ.get("LGCU_PASS_TIMES_RADIUS", "0"))  # denoiser radius (0 or 2)
 W, H = (3840, 2160) if len(sys.argv) < 3 else (int(sys.argv[1]), int(sys.argv[2]))
 ROWS = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) >= 5 else None  # time the gather stage on a row strip only
 m = scene.frame_matrices(W, H)
@@ -28,12 +29,12 @@ r.upload_objects(objects.ctypes.data, len(objects))
 r.upload_light_depth(shadow.ctypes.data, 1024)
 r.sync()
 for _ in range(3):
-    r.render_frame(harness.MODE_FUSED, 0, GI)
+    r.render_frame(harness.MODE_FUSED, RADIUS, GI)
 r.sync()
 acc, n = {}, 10
 if ROWS is None:
     for _ in range(n):
-        r.render_frame(harness.MODE_FUSED, 0, GI, profile=True)
+        r.render_frame(harness.MODE_FUSED, RADIUS, GI, profile=True)
         r.sync()
         for name, ms in r.profile():
             acc[name] = acc.get(name, 0.0) + ms / n
@@ -45,7 +46,7 @@ else:
     r.upload_fragments(frags.ctypes.data, frags.strides[0])
     r.upload_objects(objects.ctypes.data, len(objects))
     r.upload_light_depth(shadow.ctypes.data, 1024)
-    r.render_frame(harness.MODE_FUSED, 0, GI)
+    r.render_frame(harness.MODE_FUSED, RADIUS, GI)
     r.sync()
     with torch.cuda.stream(stream):
         for i in range(n + 3):
