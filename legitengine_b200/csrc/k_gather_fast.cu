@@ -355,30 +355,56 @@ struct PackArgs {
   int jobLevel[kMaxPackJobs], jobLight[kMaxPackJobs];       // level, 0 = depth quads / 1 = light quads
   int jobOfs[kMaxPackJobs], jobPitch[kMaxPackJobs];         // destination origin (float4) and entries per row
   int jobRowBegin[kMaxPackJobs], jobRowEnd[kMaxPackJobs];   // entry rows to (re)build
-  int jobBlockBegin[kMaxPackJobs + 1];                      // first CTA of each job (32x8 entries per CTA)
+  int jobBlockBegin[kMaxPackJobs + 1];                      // first CTA of each job (32x32 entries per CTA)
   int jobs;
 };
 
+// One CTA builds 32 x 32 entries: lane = column, every thread kPackRows vertically adjacent entries. Those share their rows — five
+// rows x two columns = 10 loads for 4 entries instead of 16 — and all of a thread's loads are issued before its first store. With one
+// entry per thread (r02x: 46 767 CTAs that each live for one DRAM round trip, 3.5 TB/s) the pass was bound by that latency, not by HBM.
+constexpr int kPackRows = 4, kPackCtaRows = 8 * kPackRows;
 __global__ void __launch_bounds__(256) packSidePyramidKernel(const __grid_constant__ PackArgs p, float4 *__restrict__ side) {
   int j = 0;
   while (j + 1 < p.jobs && (int)blockIdx.x >= p.jobBlockBegin[j + 1]) j++;
-  const int l = p.jobLevel[j], pitch = p.jobPitch[j];
+  const int l = p.jobLevel[j], pitch = p.jobPitch[j], rowEnd = p.jobRowEnd[j];
   const int bx = (pitch + 31) / 32, b = blockIdx.x - p.jobBlockBegin[j];
-  const int qx = (b % bx) * 32 + (threadIdx.x & 31), qy = p.jobRowBegin[j] + (b / bx) * 8 + (threadIdx.x >> 5);
-  if (qx >= pitch || qy >= p.jobRowEnd[j]) return;
+  const int qx = (b % bx) * 32 + (threadIdx.x & 31), qy0 = p.jobRowBegin[j] + (b / bx) * kPackCtaRows + (threadIdx.x >> 5) * kPackRows;
+  if (qx >= pitch || qy0 >= rowEnd) return;
+  // entry (qx, qy) = taps (x0, y0) (x1, y0) (x0, y1) (x1, y1) with y0 = clamp(qy - 1), y1 = clamp(qy): row k of the thread = clamp(qy0 - 1 + k)
   if (!p.jobLight[j]) {
     const LevelView lv = p.moments.lv[l];
-    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
-    const float *r0 = reinterpret_cast<const float *>(lv.ptr + (size_t)y0 * lv.pitch), *r1 = reinterpret_cast<const float *>(lv.ptr + (size_t)y1 * lv.pitch);
-    side[(size_t)p.jobOfs[j] + (size_t)qy * pitch + qx] = make_float4(__ldg(r0 + 2 * x0), __ldg(r0 + 2 * x1), __ldg(r1 + 2 * x0), __ldg(r1 + 2 * x1));
+    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1);
+    float t0[kPackRows + 1], t1[kPackRows + 1];
+#pragma unroll
+    for (int k = 0; k <= kPackRows; k++) {
+      const float *row = reinterpret_cast<const float *>(lv.ptr + (size_t)min(max(qy0 - 1 + k, 0), lv.h - 1) * lv.pitch);
+      t0[k] = __ldg(row + 2 * x0);
+      t1[k] = __ldg(row + 2 * x1);
+    }
+    float4 *dst = side + (size_t)p.jobOfs[j] + (size_t)qy0 * pitch + qx;
+#pragma unroll
+    for (int e = 0; e < kPackRows; e++)
+      if (qy0 + e < rowEnd) dst[(size_t)e * pitch] = make_float4(t0[e], t1[e], t0[e + 1], t1[e + 1]);
   } else {
     const LevelView lv = p.light.lv[l];
-    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1), y0 = max(qy - 1, 0), y1 = min(qy, lv.h - 1);
-    const float4 t00 = Texel<F16>::load(lv, x0, y0), t10 = Texel<F16>::load(lv, x1, y0), t01 = Texel<F16>::load(lv, x0, y1), t11 = Texel<F16>::load(lv, x1, y1);
-    float4 *dst = side + (size_t)p.jobOfs[j] + 3 * ((size_t)qy * pitch + qx);
-    dst[0] = make_float4(t00.x, t00.y, t00.z, t10.x);
-    dst[1] = make_float4(t10.y, t10.z, t01.x, t01.y);
-    dst[2] = make_float4(t01.z, t11.x, t11.y, t11.z);
+    const int x0 = max(qx - 1, 0), x1 = min(qx, lv.w - 1);
+    uint2 t0[kPackRows + 1], t1[kPackRows + 1];
+#pragma unroll
+    for (int k = 0; k <= kPackRows; k++) {
+      const uint2 *row = reinterpret_cast<const uint2 *>(lv.ptr + (size_t)min(max(qy0 - 1 + k, 0), lv.h - 1) * lv.pitch);
+      t0[k] = __ldg(row + x0);
+      t1[k] = __ldg(row + x1);
+    }
+    float4 *dst = side + (size_t)p.jobOfs[j] + 3 * ((size_t)qy0 * pitch + qx);
+#pragma unroll
+    for (int e = 0; e < kPackRows; e++) {
+      if (qy0 + e >= rowEnd) break;
+      const float4 t00 = Texel<F16>::unpack(t0[e]), t10 = Texel<F16>::unpack(t1[e]), t01 = Texel<F16>::unpack(t0[e + 1]), t11 = Texel<F16>::unpack(t1[e + 1]);
+      float4 *d = dst + 3 * (size_t)e * pitch;
+      d[0] = make_float4(t00.x, t00.y, t00.z, t10.x);
+      d[1] = make_float4(t10.y, t10.z, t01.x, t01.y);
+      d[2] = make_float4(t01.z, t11.x, t11.y, t11.z);
+    }
   }
 }
 
@@ -529,7 +555,7 @@ cudaError_t launchGatherPack(const GatherArgs &a, void *scratch, cudaStream_t s)
       p.jobRowBegin[j] = r0;
       p.jobRowEnd[j] = r1;
       p.jobBlockBegin[j] = blocks;
-      blocks += ((geom[l].quadPitch + 31) / 32) * ((r1 - r0 + 7) / 8);
+      blocks += ((geom[l].quadPitch + 31) / 32) * ((r1 - r0 + kPackCtaRows - 1) / kPackCtaRows);
     }
   p.jobBlockBegin[p.jobs] = blocks;
   if (blocks == 0) return cudaSuccess;

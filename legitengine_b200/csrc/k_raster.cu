@@ -45,9 +45,11 @@ struct __align__(16) TriRecord {
 };
 static_assert(sizeof(TriRecord) == 224, "TriRecord layout");
 
-struct BigRecord {
+struct __align__(16) BigRecord {
   uint32_t tri, firstTile, tilesX, tileCount;
+  int x0, y0, x1, y1; // copy of the triangle's pixel box: the tile path culls on it without touching the 224-byte record
 };
+static_assert(sizeof(BigRecord) == 32, "BigRecord layout");
 
 struct RasterKernelArgs {
   const lgcu_vertex *vertices;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(128) rasterSetupKernel(const __grid_constant__
     const uint32_t tilesX = (bw + kTile - 1) / kTile, tilesY = (bh + kTile - 1) / kTile;
     const unsigned long long old = atomicAdd(A.counter, (1ull << 32) | (unsigned long long)(tilesX * tilesY));
     R.big = 1;
-    A.big[old >> 32] = BigRecord{t, (uint32_t)(old & 0xffffffffull), tilesX, tilesX * tilesY};
+    A.big[old >> 32] = BigRecord{t, (uint32_t)(old & 0xffffffffull), tilesX, tilesX * tilesY, x0, y0, x1, y1};
   }
 }
 
@@ -316,14 +318,21 @@ __device__ __forceinline__ void resolveFragment(const RasterKernelArgs &A, unsig
 }
 
 // One warp per 32x16 screen tile; lane = column. kFragments: G-buffer target (fragment buffer) / depth-only target (shadow map).
-// 8 resident CTAs per SM (64 registers, some spills): the kernel is bound by the latency of its fp64 chains, not by their throughput
-// (ncu r03c: fp64 pipe 27 %, issue 34 % at 126 registers / 4 CTAs), so occupancy buys more than the spills cost — 4K G-buffer pass
-// 0.261 ms at 4 CTAs, 0.237 at 5, 0.228 at 6, 0.214 at 8 and at 10.
-template <bool kFragments>
+// 8 resident CTAs per SM (64 registers): the kernel is bound by latency, not by the fp64 pipe (ncu r03c at 126 registers / 4 CTAs: fp64
+// pipe 27 %, issue 34 %; 4K G-buffer pass 0.261 ms at 4 CTAs, 0.237 at 5, 0.228 at 6, 0.214 at 8 and at 10). Where the latency was
+// (r03c, per-instruction stall samples): 27 % of all samples waited for the 16 visibility-buffer loads of the resolve, one after the other
+// behind each row's arithmetic; 16 % were instruction-cache misses of the 16x unrolled resolve (2 900 of the kernel's 4 200
+// instructions); 16 % the cull loop's dependent scattered loads (big list -> record box -> record edges). Hence:
+//   * the column of keys starts from the visibility buffer (what the one-warp-per-triangle path left there) instead of merging it at the
+//     end: the 16 loads are in flight during the cull loop;
+//   * the cull tests the box from the 32-byte big record (coalesced) and touches the triangle record only for the corner test;
+//   * after the last triangle the keys are parked in shared memory and the resolve runs as a rolled loop (kResolveUnroll rows at a time).
+template <bool kFragments, int kResolveUnroll>
 __global__ void __launch_bounds__(128, 8) rasterTileKernel(const __grid_constant__ RasterKernelArgs A, lgcu_fragment *fragments, uint64_t pitch, LevelView depth) {
-  const int lane = threadIdx.x & 31;
+  __shared__ unsigned long long sBest[4][kScreenTileH][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tilesX = (A.width + kScreenTileW - 1) / kScreenTileW;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
   const int tilesY = (A.rows.y1 - A.rows.y0 + kScreenTileH - 1) / kScreenTileH;
   if (tile >= tilesX * tilesY) return;
   const int tx0 = (tile % tilesX) * kScreenTileW, ty0 = A.rows.y0 + (tile / tilesX) * kScreenTileH;
@@ -331,16 +340,20 @@ __global__ void __launch_bounds__(128, 8) rasterTileKernel(const __grid_constant
   const int x = tx0 + lane;
   unsigned long long best[kScreenTileH];
 #pragma unroll
-  for (int r = 0; r < kScreenTileH; r++) best[r] = kEmpty;
+  for (int r = 0; r < kScreenTileH; r++) best[r] = (x <= tx1 && ty0 + r <= ty1) ? A.vis[(size_t)(ty0 + r) * A.width + x] : kEmpty;
   const uint32_t nRecords = (uint32_t)(*A.counter >> 32);
   for (uint32_t base = 0; base < nRecords; base += 32) {
     // cull 32 big triangles against the tile: box overlap, then the corner test of rasterBigKernel
     bool keep = false;
     const uint32_t rec = base + lane;
+    uint32_t myTri = 0;
     if (rec < nRecords) {
-      const TriRecord &R = A.tris[A.big[rec].tri];
-      keep = R.x0 <= tx1 && R.x1 >= tx0 && R.y0 <= ty1 && R.y1 >= ty0;
+      const uint4 id = *reinterpret_cast<const uint4 *>(&A.big[rec]);
+      const int4 box = *reinterpret_cast<const int4 *>(&A.big[rec].x0);
+      myTri = id.x;
+      keep = box.x <= tx1 && box.z >= tx0 && box.y <= ty1 && box.w >= ty0;
       if (keep) {
+        const TriRecord &R = A.tris[myTri];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           const double ai = R.a[i], bi = R.b[i];
@@ -353,7 +366,7 @@ __global__ void __launch_bounds__(128, 8) rasterTileKernel(const __grid_constant
     while (mask) {
       const int bit = __ffs(mask) - 1;
       mask &= mask - 1;
-      const uint32_t tri = A.big[base + bit].tri;
+      const uint32_t tri = __shfl_sync(0xffffffffu, myTri, bit);
       const TriRecord &R = A.tris[tri];
       double a[3], b[3], c[3], Z[3], W[3];
 #pragma unroll
@@ -370,11 +383,12 @@ __global__ void __launch_bounds__(128, 8) rasterTileKernel(const __grid_constant
   }
   if (x > tx1) return;
 #pragma unroll
-  for (int r = 0; r < kScreenTileH; r++) {
+  for (int r = 0; r < kScreenTileH; r++) sBest[warp][r][lane] = best[r]; // read back by the same lane only: no barrier
+  const int rowsHere = ty1 - ty0 + 1;
+#pragma unroll(kResolveUnroll)
+  for (int r = 0; r < rowsHere; r++) {
     const int y = ty0 + r;
-    if (y > ty1) break;
-    const unsigned long long small = A.vis[(size_t)y * A.width + x]; // what the one-warp-per-triangle path left here (or kEmpty)
-    const unsigned long long key = small < best[r] ? small : best[r];
+    const unsigned long long key = sBest[warp][r][lane];
     if (kFragments)
       resolveFragment(A, key, x, y, fragments, pitch);
     else
@@ -460,10 +474,17 @@ cudaError_t launchRaster(const RasterArgs &r, int smCount, cudaStream_t s) {
   }
   if (tilePath) { // every big triangle is tested against every screen tile: only for scenes where that loop is short
     const int tiles = ((r.width + kScreenTileW - 1) / kScreenTileW) * ((rowsN + kScreenTileH - 1) / kScreenTileH);
-    if (r.fragments)
-      rasterTileKernel<true><<<(tiles + 3) / 4, 128, 0, s>>>(A, r.fragments, r.fragmentPitch, r.depth);
+    static const int unroll = getenv("LGCU_RASTER_RESOLVE_UNROLL") ? atoi(getenv("LGCU_RASTER_RESOLVE_UNROLL")) : 2; // A/B switch
+    if (!r.fragments)
+      rasterTileKernel<false, 4><<<(tiles + 3) / 4, 128, 0, s>>>(A, nullptr, 0, r.depth);
+    else if (unroll == 1)
+      rasterTileKernel<true, 1><<<(tiles + 3) / 4, 128, 0, s>>>(A, r.fragments, r.fragmentPitch, r.depth);
+    else if (unroll == 4)
+      rasterTileKernel<true, 4><<<(tiles + 3) / 4, 128, 0, s>>>(A, r.fragments, r.fragmentPitch, r.depth);
+    else if (unroll == 16)
+      rasterTileKernel<true, 16><<<(tiles + 3) / 4, 128, 0, s>>>(A, r.fragments, r.fragmentPitch, r.depth);
     else
-      rasterTileKernel<false><<<(tiles + 3) / 4, 128, 0, s>>>(A, nullptr, 0, r.depth);
+      rasterTileKernel<true, 2><<<(tiles + 3) / 4, 128, 0, s>>>(A, r.fragments, r.fragmentPitch, r.depth);
     return cudaGetLastError();
   }
   const dim3 grid((r.width + 31) / 32, (rowsN + 7) / 8);

@@ -132,14 +132,18 @@ __device__ __forceinline__ uint32_t packBgra8Srgb(float4 v) {
 // code): the result differs from the libm-grade one only where the encoded value sits within that distance of a rounding boundary,
 // and then by one code — inside the +-1 LSB bar of the swapchain. The accurate powf costs ~40 instructions per channel, which makes
 // the final composite issue-bound instead of HBM-bound (ncu r01j: issue 73 %, DRAM 41 %).
-__device__ __forceinline__ float linearToSrgbFast(float c) {
-  if (!(c > 0.0f)) c = 0.0f;
-  if (c > 1.0f) c = 1.0f;
-  return c <= 0.0031308f ? 12.92f * c : 1.055f * __powf(c, 1.0f / 2.4f) - 0.055f;
+__device__ __forceinline__ float linearToSrgbFast(float c) { // branch-free; c = 0 -> lg2 = -inf -> ex2 = 0, and the linear segment is selected
+  c = fminf(fmaxf(c, 0.0f), 1.0f); // NaN -> 0, like the comparisons of linearToSrgb
+  float l2, p;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(c)); // arguments of the power segment are >= 0.0031308: no denormal handling needed
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(l2 * (1.0f / 2.4f)));
+  return c <= 0.0031308f ? 12.92f * c : 1.055f * p - 0.055f;
 }
+__device__ __forceinline__ uint32_t unorm8Encoded(float x) { return (uint32_t)(x * 255.0f + 0.5f); } // x in [0, 1 + ulp]: the encoder's range
 template <bool kFast> __device__ __forceinline__ uint32_t packBgra8SrgbT(float4 v) {
   if (!kFast) return packBgra8Srgb(v);
-  return unorm8(linearToSrgbFast(v.z)) | (unorm8(linearToSrgbFast(v.y)) << 8) | (unorm8(linearToSrgbFast(v.x)) << 16) | (unorm8(saturatef(v.w)) << 24);
+  return unorm8Encoded(linearToSrgbFast(v.z)) | (unorm8Encoded(linearToSrgbFast(v.y)) << 8) | (unorm8Encoded(linearToSrgbFast(v.x)) << 16) |
+         (unorm8(saturatef(v.w)) << 24);
 }
 
 // ---- exact-order bilinear / trilinear (strict kernels; compile the TU with -fmad=false) ---------------------------
