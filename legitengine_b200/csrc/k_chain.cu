@@ -197,9 +197,8 @@ __global__ void __launch_bounds__(kChainThreads) frameChainsStagedKernel(const _
     blurTileStaged<kF16, 2>(tile, src, dst, x0, y0, p.rowEnd[l - 1]);
 }
 
-__global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_constant__ ChainsLaunch p) {
+__device__ __forceinline__ void blurGridCta(const ChainsLaunch &p, int b) {
   const ChainsArgs &a = p.a;
-  int b = blockIdx.x;
   const int chain = b >= p.blockBegin[1][0] ? 1 : 0;
   int l = 1;
   while (l < a.gridLevels && b >= p.blockBegin[chain][l]) l++; // level l occupies [blockBegin[l-1], blockBegin[l])
@@ -214,6 +213,27 @@ __global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_
     blurColumnR<kRG32, false>(a.radius, src, dst, x, y, rows);
   else
     blurColumnR<kF16, false>(a.radius, src, dst, x, y, rows);
+}
+
+__global__ void __launch_bounds__(kChainThreads) frameChainsKernel(const __grid_constant__ ChainsLaunch p) { blurGridCta(p, blockIdx.x); }
+
+// Tail and blur grid in ONE launch: the whole grid is launched in clusters of kTailCluster CTAs, the first two clusters are the tail
+// (they are dispatched first and walk their serial chain of small levels for ~16 us), every other CTA is a blur tile and ignores its
+// cluster. The two parts are data-independent (the tail reads chain level gridLevels and writes levels above it, the grid writes the
+// blurred levels 1..gridLevels), so the blur tiles fill the rest of the GPU while the tail runs instead of waiting behind it
+// (two launches on one stream: 15.5 us + 36 us at 4K, ncu r02k — and the tail costs the same on a multi-GPU strip).
+// blurBlocks CTAs of blur work follow the tail; the grid is padded to a multiple of the cluster size.
+__global__ void __cluster_dims__(kTailCluster, 1, 1) __launch_bounds__(kChainThreads, 3) frameChainsWithTailKernel(const __grid_constant__ ChainsLaunch p, int blurBlocks) {
+  if (blockIdx.x < 2 * kTailCluster) {
+    const int chain = blockIdx.x / kTailCluster, ctaRank = blockIdx.x % kTailCluster;
+    if (chain == 0)
+      chainTail<kF16>(p.a, p.a.light, p.a.blurredLight, ctaRank);
+    else
+      chainTail<kRG32>(p.a, p.a.moments, p.a.blurredMoments, ctaRank);
+    return;
+  }
+  const int b = blockIdx.x - 2 * kTailCluster;
+  if (b < blurBlocks) blurGridCta(p, b);
 }
 
 } // namespace
@@ -235,11 +255,15 @@ cudaError_t launchFrameChains(const ChainsArgs &a, cudaStream_t s) {
     p.blockBegin[chain][a.gridLevels] = blocks;
   }
   if (a.gridLevels == 0) p.blockBegin[1][0] = 0x7fffffff;
-  // Two launches on one stream, so they run one after the other (ncu r02k at 4K: tail 15.5 us, blur grid 36 us). The two are
-  // data-independent and could overlap (programmatic dependent launch, or the tail as the first clusters of one grid); at 1 % of the
-  // frame that has not been worth a second synchronisation scheme yet.
-  if (a.levels > a.gridLevels + 1) chainTailKernel<<<2 * kTailCluster, kChainThreads, 0, s>>>(a);
   static const bool staged = getenv("LGCU_BLUR_SMEM") && atoi(getenv("LGCU_BLUR_SMEM")) != 0; // A/B switch (radius 2 only)
+  static const bool split = getenv("LGCU_CHAINS_SPLIT") && atoi(getenv("LGCU_CHAINS_SPLIT")) != 0; // A/B switch: tail and grid as two launches
+  const bool tail = a.levels > a.gridLevels + 1;
+  if (tail && blocks > 0 && !staged && !split) {
+    const int grid = 2 * kTailCluster + (blocks + kTailCluster - 1) / kTailCluster * kTailCluster;
+    frameChainsWithTailKernel<<<grid, kChainThreads, 0, s>>>(p, blocks);
+    return cudaGetLastError();
+  }
+  if (tail) chainTailKernel<<<2 * kTailCluster, kChainThreads, 0, s>>>(a);
   if (blocks > 0 && staged && a.radius == 2)
     frameChainsStagedKernel<<<blocks, kChainThreads, 0, s>>>(p);
   else if (blocks > 0)

@@ -1,15 +1,16 @@
 #!/bin/bash
-# A/B of the r04 changes (raster tile kernel v2, slim K6+K7, 4-entry pack) on one B200: targeted parity tests, then per-pass times.
+# A/B of the r04b changes (tail + blur grid in one cluster launch, L1 prefetch in the frame front) on one B200, and an ncu --set full
+# capture of the kernels this round touched.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -k "raster or bundled or denoise or final or pack or chained or golden or aux or gi_gather" > gpurun_out/r04a_pytest.log 2>&1
-echo "pytest rc=$?"; tail -3 gpurun_out/r04a_pytest.log
+python -m pytest tests -m gpu -x -q -k "chain or front or golden or chained or rendergraph or strips or full_size" > gpurun_out/r04b_pytest.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/r04b_pytest.log
 run() { echo "== $*"; env "$@" python scripts/raster_times.py 2>&1 | tail -1; }
 {
 run A=default
-run LGCU_RASTER_RESOLVE_UNROLL=1
-run LGCU_RASTER_RESOLVE_UNROLL=4
-run LGCU_RASTER_RESOLVE_UNROLL=16
-run LGCU_FINAL_ROWS=1
+run LGCU_CHAINS_SPLIT=1
+run LGCU_FRONT_PREFETCH=0
 run A=default2
-} > gpurun_out/r04a_times.txt 2>&1
-cat gpurun_out/r04a_times.txt
+} > gpurun_out/r04b_times.txt 2>&1
+cat gpurun_out/r04b_times.txt
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:"rasterTileKernel|denoiseFinalGather|packSidePyramid|frameFront|frameChains" -c 14 -o gpurun_out/r04b_small_kernels python scripts/raster_times.py > gpurun_out/r04b_ncu.log 2>&1
+echo "ncu rc=$?"; ls -la gpurun_out/r04b_small_kernels.ncu-rep
