@@ -743,6 +743,7 @@ def run_strips(args, rank: int, world: int, local_rank: int):
         npx = W * H
         peak, peak_src = measured_peak_gbs()
         frame_bytes = FRAME_BYTES_PER_PX * npx + SHADOW_MAP_BYTES * world
+        fused_exchange = args.transport == "p2p" and not args.unfused_exchange
         line = {
             "metric": METRIC, "value": npx / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -761,8 +762,11 @@ def run_strips(args, rank: int, world: int, local_rank: int):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "input": "scene as the reference holds it, uploaded by every rank from host memory every step and rasterised for the rank's own rows on the "
                              "device; output: the composited BGRA8 swapchain image from the presenting rank to pinned host memory (PCIe-bound at 8K: 133 MB per frame)"},
-            "gpu_launches": 6 * args.steps * world,
-            "kernels_per_frame": 6,
+            # per rank and frame: frame front, chains (tail clusters + blur grid, one launch), side-pyramid pack, gather, K6+K7 — plus, with the
+            # fused exchange, the four lgcu_exchange kernels (open, after front, after chains, close); the unfused / NCCL transports launch
+            # more (separate signal, wait and copy kernels) and are counted by their compute kernels only
+            "gpu_launches": (9 if fused_exchange else 5) * args.steps * world,
+            "kernels_per_frame": 9 if fused_exchange else 5,
             "single_gpu": {"ms_per_step": single_ms, "value": npx / (single_ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": extra_steps,
                            "speedup_of_this_line": single_ms / ms_per_step,
                            "note": f"the whole {W}x{H} frame on rank 0's GPU alone, measured in this run after the strip-sharded leg"},

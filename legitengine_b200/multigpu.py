@@ -150,7 +150,7 @@ class P2PStripRenderer(StripRenderer):
     FRONT, CHAINS, DELIVERED, ACK, FREE = range(5)
 
     def __init__(self, *args, direct_present: bool = True, fused_exchange: bool = True, **kwargs):
-        stream = kwargs.get("stream")
+        stream = kwargs.get("stream") or (args[5] if len(args) > 5 else None)  # StripRenderer(width, height, rank, world, dist, stream, ...)
         if not stream:
             raise ValueError("P2PStripRenderer needs an explicit CUDA stream, passed as stream=... (the same one the harness renders on)")
         super().__init__(*args, **kwargs)
