@@ -221,7 +221,7 @@ int lgcu_frame_front(const lgcu_gbuffer_builder_data *gparams, const lgcu_direct
                      void *stream);
 
 /* The rest of K3 + K4 after lgcu_frame_front, in one launch: blur (radius) of levels >= 1 of both chains and mip levels above
- * LGCU_FRONT_MIP_LEVELS (built and blurred by one CTA per chain). With a row strip, the blur reads up to `radius` rows of each
+ * LGCU_FRONT_MIP_LEVELS (built and blurred by one thread-block cluster per chain, in the same launch). With a row strip, the blur reads up to `radius` rows of each
  * level outside the strip (they must be present) and the levels above LGCU_FRONT_MIP_LEVELS are built whole from level 4. */
 int lgcu_frame_chains(const lgcu_image *directLight, const lgcu_image *blurredDirectLight, const lgcu_image *depthMoments,
                       const lgcu_image *blurredDepthMoments, int32_t radius, const lgcu_rows *rows, void *stream);
