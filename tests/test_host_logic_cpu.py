@@ -65,3 +65,36 @@ def test_floor_by_magic_constant_matches_floor():
     assert np.array_equal(got, np.floor(u.astype(np.float64)).astype(np.int32))
     frac = u.astype(np.float64) - (t - magic)
     assert np.all((frac >= 0.0) & (frac < 1.0))
+
+
+def test_atan2_polynomial_error_bound():
+    """k_gather_fast.cu: atan2Poly (8-term odd minimax polynomial on [0, 1] + octant reduction) — the kernel's comment claims 1.2e-7 rad
+    for the polynomial; with the fp32 roundings of the evaluation the result stays within 5e-7 rad of atan2, i.e. two ulps at pi."""
+    coeff = [-0.004054398275911808, 0.021862303838133812, -0.055911313742399216, 0.09642116725444794, -0.13908594846725464,
+             0.1994655728340149, -0.33329859375953674, 0.9999993443489075]
+    rng = np.random.default_rng(11)
+    ang = rng.uniform(-np.pi, np.pi, 400000)
+    rad = np.exp(rng.uniform(-6.0, 6.0, ang.size))
+    x, y = (rad * np.cos(ang)).astype(f32), (rad * np.sin(ang)).astype(f32)
+    keep = (x != 0) | (y != 0)
+    x, y = x[keep], y[keep]
+    ax, ay = np.abs(x), np.abs(y)
+    mn, mx = np.minimum(ax, ay), np.maximum(ax, ay)
+    t = (mn.astype(np.float64) / mx.astype(np.float64)).astype(f32)  # the kernel multiplies by rcp.approx (1 ulp): same bound class
+    s = (t.astype(np.float64) * t.astype(np.float64)).astype(f32)
+    p = np.full(t.shape, f32(coeff[0]), dtype=f32)
+    for c in coeff[1:]:
+        p = (p.astype(np.float64) * s.astype(np.float64) + c).astype(f32)  # fmaf
+    r = (p.astype(np.float64) * t.astype(np.float64)).astype(f32)
+    r = np.where(ay > ax, (f32(1.57079632679489662) - r).astype(f32), r)
+    r = np.where(x < 0, (f32(3.14159265358979324) - r).astype(f32), r)
+    r = np.copysign(r, y)
+    err = np.abs(r.astype(np.float64) - np.arctan2(y.astype(np.float64), x.astype(np.float64)))
+    assert float(err.max()) < 5e-7, float(err.max())
+    # the polynomial itself, evaluated without rounding
+    tt = np.linspace(0.0, 1.0, 200001)
+    ss = tt * tt
+    pp = np.full(tt.shape, coeff[0])
+    for c in coeff[1:]:
+        pp = pp * ss + c
+    assert float(np.abs(pp * tt - np.arctan(tt)).max()) < 1.3e-7
